@@ -1,0 +1,18 @@
+// tcgen05 / TMEM / TMA (bf16) MLP path: interface used by api.cu and pipeline.cu
+#pragma once
+#include "common.cuh"
+
+namespace knerf {
+
+bool tc_path_compiled();
+int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training);   // -1: shape unsupported
+int64_t tc_packed_weight_bytes(const Model& m);
+int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st);
+// (o,d,t) -> rgbsigma[R*S,4]; training keeps activations in ws
+int tc_forward(const Model& m, const float* params, const void* packed, const float* o, const float* d,
+               const float* t, int64_t R, int S, bool training, float* rgbsigma, char* ws, int64_t ws_bytes,
+               cudaStream_t st);
+int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
+                float* grads, char* ws, int64_t ws_bytes, cudaStream_t st);
+
+}  // namespace knerf

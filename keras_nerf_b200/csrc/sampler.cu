@@ -1,0 +1,237 @@
+// a8 + the sort of a9: inverse-CDF hierarchical resampling and merge with the coarse depths
+// (keras_nerf/model/nerf/utils.py:60-97; keras_nerf/model/nerf/nerf.py:182-191).
+//
+// One warp per ray.  pdf/cdf: warp-shuffle inclusive scan over 32-sample blocks with a carried prefix,
+// staged in shared memory; searchsorted(side='right') = per-lane upper-bound binary search over the
+// staged cdf (== "count of cdf_j <= u" because the cdf is non-decreasing); the Nf fine samples are
+// bitonic-sorted in registers (P per lane) and rank-merged with the already ascending coarse depths,
+// so the Nc+Nf output row is written once, coalesced.
+// HBM bytes per ray (algorithmic): 8*Nc + 4*Nf read, 4*(Nc+Nf) written.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace knerf {
+
+constexpr int kSampWarps = 4;
+
+template <int P>
+__device__ __forceinline__ void bitonic_sort_regs(float (&v)[P], int lane) {
+  // element index e = lane*P + r ; ascending over e
+#pragma unroll
+  for (int k = 2; k <= 32 * P; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= P) {
+        const int lj = j / P;
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+          const int e = lane * P + r;
+          const bool up = (e & k) == 0;
+          const bool lower = (e & j) == 0;
+          const float o = __shfl_xor_sync(kFullMask, v[r], lj);
+          const float mn = fminf(v[r], o), mx = fmaxf(v[r], o);
+          v[r] = (lower == up) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+          if ((r & j) == 0) {
+            const int e = lane * P + r;
+            const bool up = (e & k) == 0;
+            const float a = v[r], b = v[r | j];
+            const float mn = fminf(a, b), mx = fmaxf(a, b);
+            v[r] = up ? mn : mx;
+            v[r | j] = up ? mx : mn;
+          }
+        }
+      }
+    }
+  }
+}
+
+struct SampleArgs {
+  const float* t_coarse; const float* mid_points; const float* weights; const float* u;
+  uint64_t seed; const float* cdf_in; int64_t R; int Nc; int Nf; int oob_mode;
+  float* t_sorted; float* samples; int32_t* indices; float* cdf_out; int32_t* oob_count;
+  int smem_per_warp;   // floats
+};
+
+template <int NCB, int P>
+__global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int Nc = a.Nc, Nf = a.Nf;
+  const int nc1 = (Nc + 1 + 3) & ~3;
+  float* cdf = smem + (size_t)wib * a.smem_per_warp;   // [Nc+1]
+  float* midp = cdf + nc1;                             // [Nc+1]: Nc-1 mid points + 2 out-of-range slots
+  float* tcs = midp + nc1;                             // [Nc]
+  float* fs = tcs + ((Nc + 3) & ~3);                   // [32*P] sorted fine samples
+  float* outs = fs + 32 * P;                           // [Nc+Nf]
+  const int64_t warp0 = (int64_t)blockIdx.x * kSampWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kSampWarps;
+
+  for (int64_t ray = warp0; ray < a.R; ray += nwarps) {
+    // ---- pdf / cdf (utils.py:63-69) -----------------------------------------------------------
+    float w[NCB], tc[NCB];
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCB; ++j) {
+      const int i = j * 32 + lane;
+      const bool valid = i < Nc;
+      w[j] = valid ? __fadd_rn(ld_stream(a.weights + ray * Nc + i), 1e-5f) : 0.f;   // weights += 1e-5
+      tc[j] = (valid && a.t_coarse != nullptr) ? ld_stream(a.t_coarse + ray * Nc + i) : 0.f;
+      part += w[j];
+    }
+    const float total = warp_sum(part);
+    if (a.cdf_in == nullptr) {
+      float carry = 0.f;
+#pragma unroll
+      for (int j = 0; j < NCB; ++j) {
+        const int i = j * 32 + lane;
+        const float pdf = __fdiv_rn(w[j], total);
+        const float incl = warp_scan_add(pdf, lane);
+        if (i < Nc) cdf[i + 1] = carry + incl;
+        carry += __shfl_sync(kFullMask, incl, 31);
+      }
+      if (lane == 0) cdf[0] = 0.f;
+    } else {
+      for (int i = lane; i <= Nc; i += 32) cdf[i] = a.cdf_in[ray * (Nc + 1) + i];
+    }
+    // ---- mid points (nerf.py:182-183) + the two out-of-range gather slots (App. C-1) -----------
+    if (a.t_coarse != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NCB; ++j) {
+        const int i = j * 32 + lane;
+        float tn = __shfl_down_sync(kFullMask, tc[j], 1);
+        if (j + 1 < NCB) {
+          const float first_next = __shfl_sync(kFullMask, tc[(j + 1 < NCB) ? j + 1 : j], 0);
+          if (lane == 31) tn = first_next;
+        }
+        if (i < Nc - 1) midp[i] = 0.5f * __fadd_rn(tn, tc[j]);
+        if (i < Nc) tcs[i] = tc[j];
+      }
+    } else {
+      for (int i = lane; i < Nc - 1; i += 32) midp[i] = a.mid_points[ray * (Nc - 1) + i];
+    }
+    __syncwarp();
+    if (lane < 2) midp[Nc - 1 + lane] = (a.oob_mode == KNERF_OOB_CLAMP && Nc >= 2) ? midp[Nc - 2] : 0.f;
+    if (a.cdf_out != nullptr)
+      for (int i = lane; i <= Nc; i += 32) a.cdf_out[ray * (Nc + 1) + i] = cdf[i];
+    __syncwarp();
+
+    // ---- inverse-CDF samples (utils.py:72-94) ---------------------------------------------------
+    float s[P];
+    int oob = 0;
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+      const int f = r * 32 + lane;
+      s[r] = CUDART_INF_F;
+      if (f < Nf) {
+        const int64_t e = ray * Nf + f;
+        const float uu = (a.u != nullptr) ? ld_stream(a.u + e) : philox_uniform(a.seed, (uint64_t)e);
+        int lo = 0, hi = Nc + 1;                      // searchsorted(cdf, u, side='right')
+        while (lo < hi) {
+          const int m = (lo + hi) >> 1;
+          if (cdf[m] <= uu) lo = m + 1; else hi = m;
+        }
+        const int idx = lo;
+        const int below = max(idx - 1, 0);            // utils.py:78
+        const int above = min(idx, Nc);               // utils.py:79 (cdf.shape[-1]-1 == Nc)
+        const float c0 = cdf[below], c1 = cdf[above];
+        const float m0 = midp[below], m1 = midp[above];
+        if (above >= Nc - 1) oob = 1;
+        float den = __fsub_rn(c1, c0);
+        if (den < 1e-5f) den = 1.0f;                  // utils.py:91
+        const float tt = __fdiv_rn(__fsub_rn(uu, c0), den);
+        s[r] = __fadd_rn(m0, __fmul_rn(tt, __fsub_rn(m1, m0)));   // utils.py:93-94
+        if (a.samples != nullptr) a.samples[e] = s[r];
+        if (a.indices != nullptr) a.indices[e] = idx;
+      }
+    }
+    if (a.oob_mode == KNERF_OOB_COUNT && a.oob_count != nullptr) {
+      const unsigned any = __ballot_sync(kFullMask, oob);
+      if (lane == 0 && any) atomicAdd(a.oob_count, 1);   // rays (not samples) with an out-of-range gather
+    }
+    if (a.t_sorted == nullptr) { __syncwarp(); continue; }
+
+    // ---- sort(concat(t_coarse, samples)) (nerf.py:190-191) -------------------------------------
+    bitonic_sort_regs<P>(s, lane);
+#pragma unroll
+    for (int r = 0; r < P; ++r) fs[lane * P + r] = s[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+      const int e = lane * P + r;
+      if (e < Nf) {
+        const float v = s[r];
+        int lo = 0, hi = Nc;                          // coarse entries <= v
+        while (lo < hi) { const int m = (lo + hi) >> 1; if (tcs[m] <= v) lo = m + 1; else hi = m; }
+        outs[e + lo] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCB; ++j) {
+      const int i = j * 32 + lane;
+      if (i < Nc) {
+        const float v = tc[j];
+        int lo = 0, hi = Nf;                          // fine entries < v
+        while (lo < hi) { const int m = (lo + hi) >> 1; if (fs[m] < v) lo = m + 1; else hi = m; }
+        outs[i + lo] = v;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < Nc + Nf; i += 32) a.t_sorted[ray * (Nc + Nf) + i] = outs[i];
+    __syncwarp();
+  }
+}
+
+}  // namespace knerf
+
+using namespace knerf;
+
+template <int NCB>
+static int launch_sampler(const SampleArgs& a, int P, int grid, size_t smem, cudaStream_t st) {
+#define KN_LAUNCH_P(PP)                                                                             \
+  case PP:                                                                                          \
+    KN_CUDA(cudaFuncSetAttribute(sample_fine_kernel<NCB, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem));                                                       \
+    sample_fine_kernel<NCB, PP><<<grid, kSampWarps * 32, smem, st>>>(a);                            \
+    break;
+  switch (P) {
+    KN_LAUNCH_P(1) KN_LAUNCH_P(2) KN_LAUNCH_P(4) KN_LAUNCH_P(8) KN_LAUNCH_P(16)
+    default: return fail(KNERF_ERR_INVALID, "knerf_sample_fine: Nf too large");
+  }
+#undef KN_LAUNCH_P
+  KN_LAUNCH_CHECK();
+  return KNERF_OK;
+}
+
+extern "C" int knerf_sample_fine(const float* t_coarse, const float* mid_points, const float* weights,
+                                 const float* u, uint64_t seed, const float* cdf_in, int64_t R, int Nc,
+                                 int Nf, int oob_mode, float* t_sorted, float* samples, int32_t* indices,
+                                 float* cdf_out, int32_t* oob_count, void* stream) {
+  KN_CHECK_ARG(weights != nullptr && R >= 0, "knerf_sample_fine: null weights");
+  KN_CHECK_ARG((t_coarse != nullptr) != (mid_points != nullptr),
+               "knerf_sample_fine: pass either t_coarse or mid_points");
+  KN_CHECK_ARG(Nc >= 2 && Nc <= 256 && Nf >= 1 && Nf <= 512, "knerf_sample_fine: Nc=%d (2..256) Nf=%d (1..512)", Nc, Nf);
+  KN_CHECK_ARG(t_sorted == nullptr || t_coarse != nullptr, "knerf_sample_fine: t_sorted needs t_coarse");
+  KN_CHECK_ARG(oob_mode >= 0 && oob_mode <= 2, "knerf_sample_fine: bad oob_mode %d", oob_mode);
+  if (R == 0) return KNERF_OK;
+  int P = 1;
+  while (32 * P < Nf) P <<= 1;
+  const int ncb = (Nc + 31) / 32;
+  SampleArgs a{t_coarse, mid_points, weights, u, seed, cdf_in, R, Nc, Nf, oob_mode,
+               t_sorted, samples, indices, cdf_out, oob_count, 0};
+  const int nc1 = (Nc + 1 + 3) & ~3;
+  a.smem_per_warp = 2 * nc1 + ((Nc + 3) & ~3) + 32 * P + ((Nc + Nf + 3) & ~3);
+  const size_t smem = (size_t)a.smem_per_warp * kSampWarps * sizeof(float);
+  const int grid = (int)std::min<int64_t>(cdiv(R, kSampWarps), (int64_t)kNumSMs * 12);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ncb) {
+    case 1: return launch_sampler<1>(a, P, grid, smem, st);
+    case 2: return launch_sampler<2>(a, P, grid, smem, st);
+    case 3: case 4: return launch_sampler<4>(a, P, grid, smem, st);
+    default: return launch_sampler<8>(a, P, grid, smem, st);
+  }
+}

@@ -1,0 +1,415 @@
+"""NeRF (reference: keras_nerf/model/nerf/nerf.py) -- same constructor / compile / train_step /
+test_step / predict_and_render_images / save_model / load_model signatures, running on libknerf.
+
+Differences that are visible to a caller (all additive):
+  * tensors are torch CUDA tensors (numpy / CPU tensors are accepted as inputs);
+  * `precision` ("fp32" = SIMT parity mode, "bf16" = tcgen05 tensor-core mode) and `oob_mode`
+    ("zero" = TF-GPU gather semantics, the parity default) constructor keywords;
+  * `u_fine=` keywords expose the uniform draws the reference takes from tf.random.uniform;
+  * data parallelism = one process per GPU; pass `strategy=RayShardedStrategy()` (or just initialise
+    torch.distributed) and the accumulated gradients are SUM-all-reduced over NCCL before Adam, which is
+    what tf.distribute.MirroredStrategy does inside apply_gradients (train.py:75,110; nerf.py:455-458).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import json
+import logging
+import os
+
+import numpy as np
+import torch
+
+from ... import _lib
+from .mlp import NeRFMLP
+from .utils import NeRFUtils
+
+
+class Adam:
+    """Keras `optimizer='adam'` defaults: lr 1e-3, beta_1 0.9, beta_2 0.999, epsilon 1e-7, no amsgrad."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.m = self.v = None
+
+    def clone(self):
+        return Adam(self.learning_rate, self.beta_1, self.beta_2, self.epsilon)
+
+    def apply_flat(self, params: torch.Tensor, grads: torch.Tensor, zero_grads=True):
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(params), torch.zeros_like(params)
+        self.iterations += 1
+        _lib.call("knerf_adam_step", _lib.ptr(params), _lib.ptr(grads), _lib.ptr(self.m), _lib.ptr(self.v),
+                  params.numel(), float(self.learning_rate), float(self.beta_1), float(self.beta_2),
+                  float(self.epsilon), self.iterations, int(zero_grads), _lib.stream())
+
+
+def get_optimizer(identifier):
+    if isinstance(identifier, Adam):
+        return identifier.clone()
+    if isinstance(identifier, str) and identifier.lower() == "adam":
+        return Adam()
+    if hasattr(identifier, "learning_rate"):   # duck-typed Keras-style Adam config
+        g = lambda k, d: float(getattr(identifier, k, d))  # noqa: E731
+        return Adam(g("learning_rate", 1e-3), g("beta_1", 0.9), g("beta_2", 0.999), g("epsilon", 1e-7))
+    raise NotImplementedError(f"optimizer {identifier!r}: only Adam is implemented (the reference scripts use 'adam')")
+
+
+class Mean:
+    """tf.keras.metrics.Mean stand-in (nerf.py:167-173)."""
+
+    def __init__(self, name=None):
+        self.name, self.total, self.count = name, 0.0, 0
+
+    def update_state(self, values):
+        v = torch.as_tensor(values, dtype=torch.float32).reshape(-1)
+        self.total += float(v.sum())
+        self.count += int(v.numel())
+
+    def result(self):
+        return self.total / max(self.count, 1)
+
+    def reset_state(self):
+        self.total, self.count = 0.0, 0
+
+    reset_states = reset_state
+
+
+def _psnr(a, b):
+    """tf.image.psnr(a, b, max_val=1.0) per image (nerf.py:309,311)."""
+    m = ((a - b) ** 2).reshape(a.shape[0], -1).mean(dim=1)
+    return -10.0 * torch.log10(m)
+
+
+def _ssim(a, b, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03):
+    """tf.image.ssim(a, b, max_val=1.0) per image (nerf.py:310,312); host-side torch glue, off the hot path."""
+    if min(a.shape[1], a.shape[2]) < filter_size:
+        return torch.full((a.shape[0],), float("nan"), device=a.device)
+    a, b = a.permute(0, 3, 1, 2), b.permute(0, 3, 1, 2)
+    ch = a.shape[1]
+    g = torch.arange(filter_size, dtype=torch.float32, device=a.device) - (filter_size - 1) / 2.0
+    g = torch.exp(-(g * g) / (2.0 * filter_sigma * filter_sigma))
+    g = g / g.sum()
+    k = (g[:, None] * g[None, :]).expand(ch, 1, filter_size, filter_size).contiguous()
+    conv = lambda x: torch.nn.functional.conv2d(x, k, groups=ch)  # noqa: E731
+    c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
+    mu_a, mu_b = conv(a), conv(b)
+    s_aa, s_bb, s_ab = conv(a * a) - mu_a * mu_a, conv(b * b) - mu_b * mu_b, conv(a * b) - mu_a * mu_b
+    lum = (2 * mu_a * mu_b + c1) / (mu_a * mu_a + mu_b * mu_b + c1)
+    cs = (2 * s_ab + c2) / (s_aa + s_bb + c2)
+    return (lum * cs).mean(dim=(1, 2, 3))
+
+
+_seed_counter = itertools.count(0xC0A45E00)
+
+
+class NeRF:
+    def __init__(self, n_coarse: int = 64, n_fine: int = 128, pos_emb_xyz: int = 10, pos_emb_dir: int = 4,
+                 n_layers: int = 8, dense_units: int = 256, skip_layer=4, model_path: str = None,
+                 precision: str = "fp32", oob_mode: str = "zero", device=None, strategy=None, **kwargs):
+        # keras_nerf/model/nerf/nerf.py:11-43
+        self.model_path = model_path
+        if self.model_path is None:
+            self.n_coarse, self.n_fine = n_coarse, n_fine
+            self.pos_emb_xyz, self.pos_emb_dir = pos_emb_xyz, pos_emb_dir
+            self.n_layers, self.dense_units, self.skip_layer = n_layers, dense_units, skip_layer
+        else:
+            self.load_model(model_path)
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self.precision = precision
+        self.oob_mode = oob_mode
+        self.device = torch.device(device) if device is not None else None
+        self.strategy = strategy
+        self.coarse = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
+                              name='coarse_nerf', device=device)
+        self.fine = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
+                            name='fine_nerf', device=device)
+        self.epsilon = 1e-10
+        self.run_eagerly = False
+        self._compiled = False
+
+    # ---- checkpoint (nerf.py:45-76) -----------------------------------------------------------
+    def save_model(self, path, weights_only=False):
+        model_config = {'n_coarse': self.n_coarse, 'n_fine': self.n_fine, 'pos_emb_xyz': self.pos_emb_xyz,
+                        'pos_emb_dir': self.pos_emb_dir, 'n_layers': self.n_layers,
+                        'dense_units': self.dense_units, 'skip_layer': self.skip_layer}
+        os.makedirs(path, exist_ok=True)
+        if not weights_only:
+            with open(os.path.join(path, 'model_config.json'), 'w') as f:
+                json.dump(model_config, f)
+        self.coarse.save_weights(os.path.join(path, 'coarse.h5'))
+        self.fine.save_weights(os.path.join(path, 'fine.h5'))
+
+    def load_model(self, path):
+        with open(os.path.join(path, 'model_config.json'), 'r') as f:
+            mc = json.load(f)
+        self.n_coarse, self.n_fine = mc['n_coarse'], mc['n_fine']
+        self.pos_emb_xyz, self.pos_emb_dir = mc['pos_emb_xyz'], mc['pos_emb_dir']
+        self.n_layers, self.dense_units, self.skip_layer = mc['n_layers'], mc['dense_units'], mc['skip_layer']
+
+    # ---- compile (nerf.py:78-173) -------------------------------------------------------------
+    def compile(self, optimizer, loss, batch_size, image_height, image_width, ray_chunks, white_background=False,
+                is_training=True, **kwargs):
+        self.run_eagerly = bool(kwargs.get("run_eagerly", False))
+        self.optimizer, self.loss = optimizer, loss
+        lname = (loss if isinstance(loss, str) else getattr(loss, "name", type(loss).__name__)).lower()
+        if "mean_squared" not in lname and "mse" not in lname and "meansquared" not in lname and not callable(loss):
+            raise NotImplementedError("only the mean-squared-error loss of the reference scripts is implemented")
+        self.batch_size, self.image_height, self.image_width = batch_size, image_height, image_width
+        self.white_background = white_background
+        self.ray_chunks = ray_chunks
+        self.num_rays = batch_size * image_height * image_width
+        if self.ray_chunks >= self.num_rays:
+            self.ray_chunks = self.num_rays                                        # nerf.py:95-98
+        assert self.num_rays % self.ray_chunks == 0, \
+            f'ray_chunks {self.ray_chunks} must be a divisor of the number of rays {self.num_rays}'   # nerf.py:100
+        self.sequential_chunks = self.num_rays // self.ray_chunks
+        self.device = self.device or _lib.default_device()
+        self.nerf_utils = NeRFUtils(self.batch_size, self.image_height, self.image_width, self.ray_chunks,
+                                    self.pos_emb_xyz, self.pos_emb_dir, self.white_background, device=self.device,
+                                    oob_mode=self.oob_mode)
+        self._build_model()
+        self.is_training = bool(is_training)
+        self._alloc_workspace()
+        if is_training:
+            self._initialize_training_accumulator()
+            self._initialize_optimizer_and_metrics(optimizer)
+        self._compiled = True
+
+    def _build_model(self):
+        # nerf.py:116-136 (weights created on first compile; optional load from model_path)
+        dx, dd = 3 + 6 * self.pos_emb_xyz, 3 + 6 * self.pos_emb_dir
+        for net in (self.coarse, self.fine):
+            if not net.built:
+                net.device = self.device
+                net.build(dx, dd, self.pos_emb_xyz, self.pos_emb_dir, self.n_coarse, self.n_fine)
+        self.cfg = self.coarse.cfg
+        if self.model_path is not None:
+            self.coarse.load_weights(os.path.join(self.model_path, 'coarse.h5'))
+            self.fine.load_weights(os.path.join(self.model_path, 'fine.h5'))
+        self._packed = {}
+        self._prec = _lib.PRECISIONS[self.precision]
+        if self._prec == _lib.BF16:
+            lib = _lib.load()
+            nbytes = lib.knerf_packed_weight_bytes(C.byref(self.cfg))
+            if nbytes <= 0:
+                raise _lib.KnerfError("bf16 (tcgen05) mode is not available for this configuration / build: "
+                                      + lib.knerf_last_error().decode())
+            for name in ("coarse", "fine"):
+                self._packed[name] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._repack()
+
+    def _repack(self):
+        if self._prec != _lib.BF16:
+            return
+        with torch.cuda.device(self.device):
+            for name, net in (("coarse", self.coarse), ("fine", self.fine)):
+                _lib.call("knerf_pack_weights", C.byref(self.cfg), _lib.ptr(net.params),
+                          self._packed[name].data_ptr(), _lib.stream())
+
+    def _packed_ptr(self, name):
+        return self._packed[name].data_ptr() if name in self._packed else None
+
+    def _alloc_workspace(self):
+        lib = _lib.load()
+        rows = self.ray_chunks * (self.n_coarse + self.n_fine)
+        need = lib.knerf_workspace_bytes(C.byref(self.cfg), rows, self._prec, int(self.is_training))
+        if need < 0:
+            raise _lib.KnerfError("knerf_workspace_bytes: " + lib.knerf_last_error().decode())
+        self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def _initialize_training_accumulator(self):
+        # nerf.py:138-161: one accumulator per trainable variable == one flat buffer per net here
+        n = self.coarse.params.numel()
+        self._grad_flat = torch.zeros(2 * n, dtype=torch.float32, device=self.device)   # one all-reduce buffer
+        self.coarse_gradients_accumulator = self._grad_flat[:n]
+        self.fine_gradients_accumulator = self._grad_flat[n:]
+        self._losses = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def _initialize_optimizer_and_metrics(self, optimizer):
+        # nerf.py:163-173
+        self.coarse_optimizer = get_optimizer(optimizer)
+        self.fine_optimizer = get_optimizer(optimizer)
+        self.coarse_loss_tracker = Mean(name="coarse_loss")
+        self.coarse_psnr_metric = Mean(name="coarse_psnr")
+        self.corase_ssim_metric = Mean(name="coarse_ssim")
+        self.fine_loss_tracker = Mean(name="fine_loss")
+        self.fine_psnr_metric = Mean(name="fine_psnr")
+        self.fine_ssim_metric = Mean(name="fine_ssim")
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _flat_rays(self, rays):
+        o, d, t = (_lib.dev(r, self.device) for r in rays)
+        n = self.num_rays
+        return o.reshape(n, 3), d.reshape(n, 3), t.reshape(n, self.n_coarse)
+
+    def _u(self, u_fine, n):
+        if u_fine is None:
+            return None
+        return _lib.dev(u_fine, self.device).reshape(n, self.n_fine)
+
+    # ---- rendering (nerf.py:175-304) ----------------------------------------------------------
+    def _render_rays(self, o, d, t, u_fine, seed, outs_c, outs_f, t_sorted=None):
+        R = o.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.call("knerf_render_chunk", C.byref(self.cfg), _lib.ptr(self.coarse.params), _lib.ptr(self.fine.params),
+                      self._packed_ptr("coarse"), self._packed_ptr("fine"), _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R,
+                      _lib.ptr(u_fine), int(seed), int(bool(self.white_background)),
+                      _lib.OOB_CLAMP if self.oob_mode == "clamp" else _lib.OOB_ZERO, self._prec,
+                      _lib.ptr(outs_c[0]), _lib.ptr(outs_c[1]), _lib.ptr(outs_c[2]),
+                      _lib.ptr(outs_f[0]), _lib.ptr(outs_f[1]), _lib.ptr(outs_f[2]), _lib.ptr(t_sorted),
+                      self._ws.data_ptr(), self._ws.numel(), _lib.stream())
+
+    def predict_and_render_chunk(self, ray_chunks, u_fine=None, seed=None):
+        """nerf.py:218-227: (o[R,3], d[R,3], t[R,Nc]) -> (coarse dict, fine dict)."""
+        o, d, t = (_lib.dev(r, self.device) for r in ray_chunks)
+        R = o.shape[0]
+        assert R <= self.ray_chunks, f"chunk of {R} rays exceeds compiled ray_chunks {self.ray_chunks}"
+        S = self.n_coarse + self.n_fine
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)  # noqa: E731
+        oc, of = (mk(R, 3), mk(R), mk(R, self.n_coarse)), (mk(R, 3), mk(R), mk(R, S))
+        u = None if u_fine is None else _lib.dev(u_fine, self.device).reshape(R, self.n_fine)
+        self._render_rays(o, d, t, u, next(_seed_counter) if seed is None else seed, oc, of)
+        return ({'image': oc[0], 'depth': oc[1], 'weights': oc[2]}, {'image': of[0], 'depth': of[1], 'weights': of[2]})
+
+    def predict_and_render_images(self, rays, u_fine=None, seed=None):
+        """nerf.py:229-304: rays = (o[B,H,W,3], d[B,H,W,3], t[B,H,W,Nc]) -> (coarse, fine) dicts of
+        image[B,H,W,3], depth[B,H,W], weights[B,H,W,S]."""
+        o, d, t = self._flat_rays(rays)
+        n, S = self.num_rays, self.n_coarse + self.n_fine
+        u = self._u(u_fine, n)
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)  # noqa: E731
+        ci, cd, cw = mk(n, 3), mk(n), mk(n, self.n_coarse)
+        fi, fd, fw = mk(n, 3), mk(n), mk(n, S)
+        seed = next(_seed_counter) if seed is None else seed
+        rc = self.ray_chunks
+        for i in range(self.sequential_chunks):                                   # nerf.py:251
+            s = slice(i * rc, (i + 1) * rc)
+            # Philox counters are per element of the chunk: give every chunk its own stream
+            self._render_rays(o[s], d[s], t[s], None if u is None else u[s], seed + i * 0x9E3779B1,
+                              (ci[s], cd[s], cw[s]), (fi[s], fd[s], fw[s]))
+        B, H, W = self.batch_size, self.image_height, self.image_width
+        coarse = {'image': ci.view(B, H, W, 3), 'depth': cd.view(B, H, W), 'weights': cw.view(B, H, W, self.n_coarse)}
+        fine = {'image': fi.view(B, H, W, 3), 'depth': fd.view(B, H, W), 'weights': fw.view(B, H, W, S)}
+        return coarse, fine
+
+    # ---- metrics (nerf.py:306-330) ------------------------------------------------------------
+    def update_and_return_metrics(self, images, coarse_images, fine_images, coarse_loss, fine_loss):
+        self.coarse_loss_tracker.update_state(float(coarse_loss))
+        self.coarse_psnr_metric.update_state(_psnr(images, coarse_images).cpu())
+        self.corase_ssim_metric.update_state(_ssim(images, coarse_images).cpu())
+        self.fine_loss_tracker.update_state(float(fine_loss))
+        self.fine_psnr_metric.update_state(_psnr(images, fine_images).cpu())
+        self.fine_ssim_metric.update_state(_ssim(images, fine_images).cpu())
+        return {m.name: m.result() for m in self.metrics}
+
+    # ---- training (nerf.py:332-473) -----------------------------------------------------------
+    def accumulate_gradients(self, images, rays, u_fine=None, seed=None, want_images=True):
+        """The chunk loop of train_step (nerf.py:351-421): fills the two gradient accumulators and the loss
+        accumulators; returns (coarse_images, fine_images) [B,H,W,3] (or None)."""
+        images = _lib.dev(images, self.device)[..., :3]                           # nerf.py:335
+        n = self.num_rays
+        target = images.reshape(n, 3).contiguous()
+        o, d, t = self._flat_rays(rays)
+        u = self._u(u_fine, n)
+        ci = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_images else None
+        fi = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_images else None
+        seed = next(_seed_counter) if seed is None else seed
+        rc, nch = self.ray_chunks, self.sequential_chunks
+        oob = _lib.OOB_CLAMP if self.oob_mode == "clamp" else _lib.OOB_ZERO
+        with torch.cuda.device(self.device):
+            for i in range(nch):
+                s = slice(i * rc, (i + 1) * rc)
+                _lib.call("knerf_train_chunk", C.byref(self.cfg), _lib.ptr(self.coarse.params),
+                          _lib.ptr(self.fine.params), self._packed_ptr("coarse"), self._packed_ptr("fine"),
+                          _lib.ptr(o[s]), _lib.ptr(d[s]), _lib.ptr(t[s]), _lib.ptr(target[s]), rc,
+                          None if u is None else _lib.ptr(u[s]), int(seed + i * 0x9E3779B1),
+                          int(bool(self.white_background)), oob, self._prec, 1.0 / nch,
+                          _lib.ptr(self.coarse_gradients_accumulator), _lib.ptr(self.fine_gradients_accumulator),
+                          _lib.ptr(self._losses), None if ci is None else _lib.ptr(ci[s]),
+                          None if fi is None else _lib.ptr(fi[s]), self._ws.data_ptr(), self._ws.numel(),
+                          _lib.stream())
+        B, H, W = self.batch_size, self.image_height, self.image_width
+        if not want_images:
+            return None, None
+        return ci.view(B, H, W, 3), fi.view(B, H, W, 3)
+
+    def apply_gradients(self):
+        """nerf.py:455-471: cross-replica SUM (MirroredStrategy semantics), two Adam steps, zero accumulators."""
+        if self.strategy is not None:
+            self.strategy.all_reduce_sum(self.coarse_gradients_accumulator, self.fine_gradients_accumulator)
+        with torch.cuda.device(self.device):
+            self.coarse_optimizer.apply_flat(self.coarse.params, self.coarse_gradients_accumulator, zero_grads=True)
+            self.fine_optimizer.apply_flat(self.fine.params, self.fine_gradients_accumulator, zero_grads=True)
+        self._repack()
+
+    def train_step(self, inputs, u_fine=None, seed=None):
+        images, rays = inputs
+        ci, fi = self.accumulate_gradients(images, rays, u_fine=u_fine, seed=seed)
+        losses = self._losses.clone()
+        self._losses.zero_()                                                      # nerf.py:465-466
+        if self.run_eagerly or os.environ.get("KNERF_ASSERT_FINITE"):
+            # tf.debugging.assert_all_finite on every gradient (nerf.py:381-382,410-411): one host sync
+            for name, g in (("Coarse", self.coarse_gradients_accumulator), ("Fine", self.fine_gradients_accumulator)):
+                if not bool(torch.isfinite(g).all()):
+                    raise FloatingPointError(f"{name} Gradient is not finite")
+        self.apply_gradients()
+        imgs = _lib.dev(images, self.device)[..., :3]
+        lc, lf = losses.tolist()
+        return self.update_and_return_metrics(imgs, ci, fi, lc, lf)
+
+    def test_step(self, inputs, u_fine=None, seed=None):
+        # nerf.py:475-497
+        images, rays = inputs
+        images = _lib.dev(images, self.device)[..., :3].contiguous()
+        coarse, fine = self.predict_and_render_images(rays, u_fine=u_fine, seed=seed)
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            for k, res in enumerate((coarse, fine)):
+                _lib.call("knerf_mse", _lib.ptr(images), _lib.ptr(res['image'].contiguous()), images.numel(),
+                          out[k:k + 1].data_ptr(), _lib.stream())
+        lc, lf = out.tolist()
+        return self.update_and_return_metrics(images, coarse['image'], fine['image'], lc, lf)
+
+    @property
+    def metrics(self):
+        # nerf.py:499-508
+        return [self.coarse_loss_tracker, self.coarse_psnr_metric, self.corase_ssim_metric,
+                self.fine_loss_tracker, self.fine_psnr_metric, self.fine_ssim_metric]
+
+    # ---- a thin Keras-style fit loop (train.py:151-157, train_single.py:137-143) ---------------
+    def fit(self, dataset, epochs=1, validation_data=None, callbacks=None, initial_epoch=0, verbose=1):
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            else:
+                cb.model = self
+        history = {}
+        for epoch in range(initial_epoch, epochs):
+            for m in self.metrics:
+                m.reset_state()
+            logs = {}
+            for step, batch in enumerate(dataset):
+                logs = self.train_step(batch)
+                for cb in callbacks:
+                    if hasattr(cb, "on_train_batch_end"):
+                        cb.on_train_batch_end(step, logs)
+            if validation_data is not None:
+                for m in self.metrics:
+                    m.reset_state()
+                vlogs = {}
+                for batch in validation_data:
+                    vlogs = self.test_step(batch)
+                logs = {**logs, **{"val_" + k: v for k, v in vlogs.items()}}
+            for k, v in logs.items():
+                history.setdefault(k, []).append(v)
+            if verbose:
+                logging.info("epoch %d: %s", epoch + 1, {k: round(float(v), 5) for k, v in logs.items()})
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+        return history
