@@ -44,6 +44,14 @@ typedef enum knerf_oob_mode {
   KNERF_OOB_COUNT = 2  /* as ZERO, and count offending samples into *oob_count (host raises: TF-CPU) */
 } knerf_oob_mode;
 
+/* OR-ed into every `oob_mode` argument.  tf.reduce_sum / tf.cumsum do not define a summation order
+ * (TF-CPU is sequential, TF-GPU uses a cub scan).  The default is a warp-shuffle scan; with this flag the
+ * pdf normaliser and the cdf are summed strictly left to right in fp32 (TF-CPU / NumPy order), which makes
+ * the cdf -- and through it every fine depth -- bit-identical to the CPU oracle.  The fp32 parity mode of
+ * the Python shim sets it: the out-of-range-gather quirk (App. C-1) turns a 1e-6 cdf difference into a
+ * 5e-4 depth difference for the ~3% of samples that land in [0, near).                                  */
+#define KNERF_SCAN_SEQUENTIAL 0x10
+
 typedef enum knerf_precision {
   KNERF_FP32 = 0, /* SIMT FFMA, fp32 end to end: the 1e-5 parity mode                   */
   KNERF_BF16 = 1  /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation         */

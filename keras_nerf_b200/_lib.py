@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libknerf.so")
 
 OOB_ZERO, OOB_CLAMP, OOB_COUNT = 0, 1, 2
+SCAN_SEQUENTIAL = 0x10   # OR-ed into oob_mode: pdf/cdf summed left to right (TF-CPU / NumPy order)
 FP32, BF16 = 0, 1
 PRECISIONS = {"fp32": FP32, "float32": FP32, "bf16": BF16, "bfloat16": BF16}
 OOB_MODES = {"zero": OOB_ZERO, "clamp": OOB_CLAMP, "raise": OOB_COUNT}

@@ -52,7 +52,7 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&v)[P], int lane) {
 
 struct SampleArgs {
   const float* t_coarse; const float* mid_points; const float* weights; const float* u;
-  uint64_t seed; const float* cdf_in; int64_t R; int Nc; int Nf; int oob_mode;
+  uint64_t seed; const float* cdf_in; int64_t R; int Nc; int Nf; int oob_mode; int sequential;
   float* t_sorted; float* samples; int32_t* indices; float* cdf_out; int32_t* oob_count;
   int smem_per_warp;   // floats
 };
@@ -83,8 +83,28 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
       tc[j] = (valid && a.t_coarse != nullptr) ? ld_stream(a.t_coarse + ray * Nc + i) : 0.f;
       part += w[j];
     }
+    if (a.cdf_in == nullptr && a.sequential) {
+      // TF-CPU / NumPy order: normaliser and cdf summed strictly left to right (KNERF_SCAN_SEQUENTIAL)
+#pragma unroll
+      for (int j = 0; j < NCB; ++j) {
+        const int i = j * 32 + lane;
+        if (i < Nc) outs[i] = w[j];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < Nc; ++i) tot = __fadd_rn(tot, outs[i]);
+        float run = 0.f;
+        cdf[0] = 0.f;
+        for (int i = 0; i < Nc; ++i) {
+          run = __fadd_rn(run, __fdiv_rn(outs[i], tot));
+          cdf[i + 1] = run;
+        }
+      }
+      __syncwarp();
+    }
     const float total = warp_sum(part);
-    if (a.cdf_in == nullptr) {
+    if (a.cdf_in == nullptr && !a.sequential) {
       float carry = 0.f;
 #pragma unroll
       for (int j = 0; j < NCB; ++j) {
@@ -95,7 +115,7 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
         carry += __shfl_sync(kFullMask, incl, 31);
       }
       if (lane == 0) cdf[0] = 0.f;
-    } else {
+    } else if (a.cdf_in != nullptr) {
       for (int i = lane; i <= Nc; i += 32) cdf[i] = a.cdf_in[ray * (Nc + 1) + i];
     }
     // ---- mid points (nerf.py:182-183) + the two out-of-range gather slots (App. C-1) -----------
@@ -216,12 +236,14 @@ extern "C" int knerf_sample_fine(const float* t_coarse, const float* mid_points,
                "knerf_sample_fine: pass either t_coarse or mid_points");
   KN_CHECK_ARG(Nc >= 2 && Nc <= 256 && Nf >= 1 && Nf <= 512, "knerf_sample_fine: Nc=%d (2..256) Nf=%d (1..512)", Nc, Nf);
   KN_CHECK_ARG(t_sorted == nullptr || t_coarse != nullptr, "knerf_sample_fine: t_sorted needs t_coarse");
+  const int sequential = (oob_mode & KNERF_SCAN_SEQUENTIAL) ? 1 : 0;
+  oob_mode &= ~KNERF_SCAN_SEQUENTIAL;
   KN_CHECK_ARG(oob_mode >= 0 && oob_mode <= 2, "knerf_sample_fine: bad oob_mode %d", oob_mode);
   if (R == 0) return KNERF_OK;
   int P = 1;
   while (32 * P < Nf) P <<= 1;
   const int ncb = (Nc + 31) / 32;
-  SampleArgs a{t_coarse, mid_points, weights, u, seed, cdf_in, R, Nc, Nf, oob_mode,
+  SampleArgs a{t_coarse, mid_points, weights, u, seed, cdf_in, R, Nc, Nf, oob_mode, sequential,
                t_sorted, samples, indices, cdf_out, oob_count, 0};
   const int nc1 = (Nc + 1 + 3) & ~3;
   a.smem_per_warp = 2 * nc1 + ((Nc + 3) & ~3) + 32 * P + ((Nc + Nf + 3) & ~3);

@@ -108,7 +108,8 @@ _seed_counter = itertools.count(0xC0A45E00)
 class NeRF:
     def __init__(self, n_coarse: int = 64, n_fine: int = 128, pos_emb_xyz: int = 10, pos_emb_dir: int = 4,
                  n_layers: int = 8, dense_units: int = 256, skip_layer=4, model_path: str = None,
-                 precision: str = "fp32", oob_mode: str = "zero", device=None, strategy=None, **kwargs):
+                 precision: str = "fp32", oob_mode: str = "zero", scan_mode: str = None, device=None,
+                 strategy=None, **kwargs):
         # keras_nerf/model/nerf/nerf.py:11-43
         self.model_path = model_path
         if self.model_path is None:
@@ -121,6 +122,8 @@ class NeRF:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.precision = precision
         self.oob_mode = oob_mode
+        # fp32 parity mode sums the pdf/cdf in TF-CPU order (bit-identical cdf); bf16 mode uses the warp scan
+        self.scan_mode = scan_mode or ("sequential" if precision in ("fp32", "float32") else "warp")
         self.device = torch.device(device) if device is not None else None
         self.strategy = strategy
         self.coarse = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
@@ -170,7 +173,7 @@ class NeRF:
         self.device = self.device or _lib.default_device()
         self.nerf_utils = NeRFUtils(self.batch_size, self.image_height, self.image_width, self.ray_chunks,
                                     self.pos_emb_xyz, self.pos_emb_dir, self.white_background, device=self.device,
-                                    oob_mode=self.oob_mode)
+                                    oob_mode=self.oob_mode, scan_mode=self.scan_mode)
         self._build_model()
         self.is_training = bool(is_training)
         self._alloc_workspace()
@@ -251,6 +254,10 @@ class NeRF:
             return None
         return _lib.dev(u_fine, self.device).reshape(n, self.n_fine)
 
+    def _sampler_flags(self):
+        return ((_lib.OOB_CLAMP if self.oob_mode == "clamp" else _lib.OOB_ZERO)
+                | (_lib.SCAN_SEQUENTIAL if self.scan_mode == "sequential" else 0))
+
     # ---- rendering (nerf.py:175-304) ----------------------------------------------------------
     def _render_rays(self, o, d, t, u_fine, seed, outs_c, outs_f, t_sorted=None):
         R = o.shape[0]
@@ -258,7 +265,7 @@ class NeRF:
             _lib.call("knerf_render_chunk", C.byref(self.cfg), _lib.ptr(self.coarse.params), _lib.ptr(self.fine.params),
                       self._packed_ptr("coarse"), self._packed_ptr("fine"), _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R,
                       _lib.ptr(u_fine), int(seed), int(bool(self.white_background)),
-                      _lib.OOB_CLAMP if self.oob_mode == "clamp" else _lib.OOB_ZERO, self._prec,
+                      self._sampler_flags(), self._prec,
                       _lib.ptr(outs_c[0]), _lib.ptr(outs_c[1]), _lib.ptr(outs_c[2]),
                       _lib.ptr(outs_f[0]), _lib.ptr(outs_f[1]), _lib.ptr(outs_f[2]), _lib.ptr(t_sorted),
                       self._ws.data_ptr(), self._ws.numel(), _lib.stream())
@@ -319,7 +326,7 @@ class NeRF:
         fi = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_images else None
         seed = next(_seed_counter) if seed is None else seed
         rc, nch = self.ray_chunks, self.sequential_chunks
-        oob = _lib.OOB_CLAMP if self.oob_mode == "clamp" else _lib.OOB_ZERO
+        oob = self._sampler_flags()
         with torch.cuda.device(self.device):
             for i in range(nch):
                 s = slice(i * rc, (i + 1) * rc)

@@ -13,7 +13,7 @@ _seed_counter = itertools.count(0xF17E0000)
 
 class NeRFUtils:
     def __init__(self, batch_size, image_height, image_width, ray_chunks, pos_emb_xyz, pos_emb_dir,
-                 white_background=False, device=None, oob_mode="zero"):
+                 white_background=False, device=None, oob_mode="zero", scan_mode="sequential"):
         # keras_nerf/model/nerf/utils.py:5-14
         self.batch_size = batch_size
         self.image_height = image_height
@@ -26,6 +26,9 @@ class NeRFUtils:
         self.white_background = white_background
         self.device = torch.device(device) if device is not None else None
         self.oob_mode = oob_mode
+        # "sequential": pdf normaliser / cdf summed left to right (TF-CPU order, bit-identical to the oracle);
+        # "warp": warp-shuffle scan (the throughput default of the bf16 mode)
+        self.scan_mode = scan_mode
 
     def _dev(self):
         return self.device or _lib.default_device()
@@ -72,12 +75,13 @@ class NeRFUtils:
             idx = torch.empty(lead + (n_samples,), dtype=torch.int32, device=device)
             cdf_out = torch.empty(lead + (Nc + 1,), dtype=torch.float32, device=device)
         mode = _lib.OOB_MODES[self.oob_mode]
+        flags = mode | (_lib.SCAN_SEQUENTIAL if self.scan_mode == "sequential" else 0)
         count = torch.zeros(1, dtype=torch.int32, device=device) if mode == _lib.OOB_COUNT else None
         if seed is None:
             seed = next(_seed_counter)
         with torch.cuda.device(device):
             _lib.call("knerf_sample_fine", None, _lib.ptr(mid), _lib.ptr(w), _lib.ptr(u), int(seed), _lib.ptr(cdf),
-                      R, Nc, n_samples, mode, None, _lib.ptr(samples), _lib.ptr(idx, torch.int32),
+                      R, Nc, n_samples, flags, None, _lib.ptr(samples), _lib.ptr(idx, torch.int32),
                       _lib.ptr(cdf_out), _lib.ptr(count, torch.int32), _lib.stream())
         if count is not None and int(count.item()) > 0:
             # TF's CPU gather kernel raises InvalidArgumentError here

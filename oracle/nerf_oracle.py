@@ -27,8 +27,8 @@ __all__ = [
     "get_focal_from_fov", "pose_spherical", "linspace_tf", "generate_rays",
     "positional_encoding", "encode_position_and_directions", "layer_shapes", "param_count",
     "init_params", "flatten_params", "unflatten_params", "mlp_forward",
-    "cumprod_exclusive_seq", "cumsum_seq", "render_image_depth_chunk", "fine_cdf",
-    "fine_hierarchical_sampling_chunk", "predict_and_render_chunk_single", "predict_and_render_chunk",
+    "cumprod_exclusive_seq", "cumsum_seq", "reduce_sum_seq", "render_image_depth_chunk", "fine_cdf",
+    "fine_hierarchical_sampling_chunk", "predict_and_render_chunk_single", "predict_and_render_chunk", "render_given_points",
     "predict_and_render_images", "mse", "psnr", "AdamState", "adam_apply", "train_step",
     "composite_backward_analytic", "uniform24",
 ]
@@ -268,6 +268,16 @@ def cumprod_exclusive_seq(x: torch.Tensor) -> torch.Tensor:
     return torch.stack(outs, dim=-1)
 
 
+def reduce_sum_seq(x: torch.Tensor, dim: int = -1, keepdim: bool = False) -> torch.Tensor:
+    """tf.reduce_sum along `dim`, summed strictly left to right in fp32 [TF-sem: TF leaves the order
+    unspecified; this is the documented choice shared with oracle/tfshim and KNERF_SCAN_SEQUENTIAL]."""
+    xm = x.movedim(dim, -1)
+    acc = xm[..., 0]
+    for i in range(1, xm.shape[-1]):
+        acc = acc + xm[..., i]
+    return acc.unsqueeze(dim) if keepdim else acc
+
+
 def cumsum_seq(x: torch.Tensor) -> torch.Tensor:
     """tf.cumsum(x, axis=-1) as a sequential fp32 running sum (TF CPU / numpy order)."""
     return torch.from_numpy(np.cumsum(x.detach().numpy(), axis=-1, dtype=np.float32))
@@ -287,10 +297,10 @@ def render_image_depth_chunk(rgb, sigma, t, white_background: bool, clip: bool =
     exp_alpha = 1.0 - alpha                                        # :43
     trans = cumprod_exclusive_seq(exp_alpha + eps)                 # :46-47
     weights = alpha * trans                                        # :48
-    image = (weights[..., None] * rgb).sum(dim=-2)                 # :50
-    depth = (weights * t).sum(dim=-1)                              # :51
+    image = reduce_sum_seq(weights[..., None] * rgb, dim=-2)       # :50
+    depth = reduce_sum_seq(weights * t, dim=-1)                    # :51
     if white_background:
-        image = image + (1.0 - weights.sum(dim=-1)[..., None])     # :53-54
+        image = image + (1.0 - reduce_sum_seq(weights, dim=-1)[..., None])   # :53-54
     if clip:
         image = torch.clamp(image, 0.0, 1.0)                       # :56
     return image, depth, weights
@@ -331,7 +341,7 @@ def composite_backward_analytic(rgb, sigma, t, dL_dimage, white_background: bool
 def fine_cdf(weights: torch.Tensor) -> torch.Tensor:
     """keras_nerf/model/nerf/utils.py:63-69 -- w+=1e-5; pdf=w/sum; cdf=[0,cumsum(pdf)]."""
     w = weights + torch.tensor(1e-5, dtype=F32)
-    pdf = w / w.sum(dim=-1, keepdim=True)
+    pdf = w / reduce_sum_seq(w, dim=-1, keepdim=True)
     cdf = cumsum_seq(pdf)
     return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
 
@@ -400,6 +410,18 @@ def predict_and_render_chunk_single(params, cfg: NerfConfig, o, d, t_c, white: b
            "rgb": rgb, "sigma": sigma}
     out.update(extra)
     return out
+
+
+def render_given_points(params, cfg: NerfConfig, o, d, points, white: bool):
+    """The tail of `_predict_and_render_chunk` (nerf.py:199-216) for depths that are already chosen.
+
+    Used to check the fine network + compositing (and their backward) GIVEN the reference's sorted
+    depths: end to end the fine pass is ill-conditioned (App. C-1: a 1e-7 difference in the coarse weights
+    moves the ~3% of samples that fall in [0, near) by ~1e-3), so parity is pinned stage by stage."""
+    xyz, dirs = encode_position_and_directions(o, d, points, cfg.pos_emb_xyz, cfg.pos_emb_dir)
+    rgb, sigma = mlp_forward(params, xyz, dirs, cfg)
+    image, depth, weights = render_image_depth_chunk(rgb, sigma, points, white)
+    return {"image": image, "depth": depth, "weights": weights, "rgb": rgb, "sigma": sigma}
 
 
 def predict_and_render_chunk(params_c, params_f, cfg, o, d, t_c, u_fine, white, oob_mode=OOB_ZERO):

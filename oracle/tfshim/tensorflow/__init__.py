@@ -188,10 +188,18 @@ def broadcast_to(x, shape):  # noqa: A002
 
 
 def reduce_sum(x, axis=None, keepdims=False):
+    """[TF-sem] TF does not define a summation order (Eigen tree on CPU, cub on GPU); the stand-in sums
+    strictly left to right in fp32 along `axis` so that the order is a documented, reproducible choice."""
     x = _c(x)
     if axis is None:
         return x.sum()
-    return x.sum(dim=axis, keepdim=keepdims)
+    xm = x.movedim(axis, -1)
+    acc = xm[..., 0]
+    for i in _builtin_range(1, xm.shape[-1]):
+        acc = acc + xm[..., i]
+    if keepdims:
+        acc = acc.unsqueeze(axis)
+    return acc.as_subclass(Tensor)
 
 
 def reduce_mean(x, axis=None, keepdims=False):
