@@ -66,6 +66,8 @@ typedef struct knerf_config {
 
 int knerf_abi_version(void);
 const char* knerf_last_error(void);
+/* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches) */
+uint64_t knerf_launch_count(void);
 /* 1 if the library contains the tcgen05 path and the current device is sm_100 */
 int knerf_device_supports_bf16(void);
 

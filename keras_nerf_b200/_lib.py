@@ -37,6 +37,7 @@ _CFG = C.POINTER(Config)
 SIGNATURES = {
     "knerf_abi_version": (_I, []),
     "knerf_last_error": (C.c_char_p, []),
+    "knerf_launch_count": (_U64, []),
     "knerf_device_supports_bf16": (_I, []),
     "knerf_generate_rays": (_I, [_P, _I, _I, _F, _F, _F, _I, _P, _U64, _P, _P, _P, _P]),
     "knerf_uniform": (_I, [_P, _L, _U64, _U64, _P]),

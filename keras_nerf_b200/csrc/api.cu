@@ -3,7 +3,12 @@
 #include "mlp_fp32.cuh"
 #include "mlp_tc.cuh"
 
+#include <atomic>
+
 namespace knerf {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 char* last_error_buffer() {
   static thread_local char buf[512] = {0};
@@ -63,6 +68,7 @@ bool is_flagship(const Model& m) {
 using namespace knerf;
 
 extern "C" int knerf_abi_version(void) { return KNERF_ABI_VERSION; }
+extern "C" uint64_t knerf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* knerf_last_error(void) { return last_error_buffer(); }
 
 extern "C" int knerf_device_supports_bf16(void) {

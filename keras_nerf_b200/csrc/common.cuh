@@ -29,7 +29,12 @@ int fail(int code, const char* fmt, ...);
                            __FILE__, __LINE__);                                                   \
   } while (0)
 
-#define KN_LAUNCH_CHECK() KN_CUDA(cudaGetLastError())
+void count_launch();
+#define KN_LAUNCH_CHECK()          \
+  do {                             \
+    ::knerf::count_launch();       \
+    KN_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define KN_TRY(expr)            \
   do {                          \

@@ -1,0 +1,57 @@
+"""Synthetic nerf_synthetic-shaped scene (the dataset is not available offline).
+
+Procedural orbit poses exactly like inference.py:61-67 (pose_spherical(theta, phi=-30, t=4.0)), fov of the lego
+scene, near 2 / far 6, and ANALYTIC target images: a ray-traced unit sphere with normal shading,
+alpha-composited onto white/black exactly like keras_nerf/data/image.py:25-33.  Replaces DatasetLoader
+(loader.py:55-113) for benchmarks and tests; host-side glue (torch ops), not part of the hot path."""
+from __future__ import annotations
+
+import torch
+
+from .rays import RaysGenerator
+from .utils import get_focal_from_fov, pose_spherical
+
+LEGO_FOV = 0.6911112070083618
+
+
+def analytic_rgba(o: torch.Tensor, d: torch.Tensor, white_background: bool = True) -> torch.Tensor:
+    """o, d [...,3] -> RGBA [...,4] of a unit sphere at the origin, composited like image.py:25-33."""
+    b = (o * d).sum(-1)
+    c = (o * o).sum(-1) - 1.0
+    disc = b * b - c
+    hit = disc > 0
+    t = -b - torch.sqrt(disc.clamp_min(0))
+    n = torch.nn.functional.normalize(o + d * t[..., None], dim=-1)
+    rgb = (0.5 * (n + 1.0)).clamp(0, 1)
+    alpha = hit.to(o.dtype)[..., None]
+    bg = torch.ones_like(rgb) if white_background else torch.zeros_like(rgb)
+    img = alpha * rgb + (1.0 - alpha) * bg
+    return torch.cat([img, alpha], dim=-1).clamp(0, 1)
+
+
+class SyntheticScene:
+    def __init__(self, image_wh: int, n_coarse: int, n_views: int = 100, phi: float = -30.0, radius: float = 4.0,
+                 near: float = 2.0, far: float = 6.0, white_background: bool = True, device=None):
+        self.wh, self.n_views, self.phi, self.radius = image_wh, n_views, phi, radius
+        self.white = white_background
+        self.focal = get_focal_from_fov(LEGO_FOV, image_wh)
+        self.gen = RaysGenerator(self.focal, image_wh, image_wh, near, far, n_coarse, device=device)
+
+    def pose(self, k: int):
+        return pose_spherical(360.0 * (k % self.n_views) / self.n_views, self.phi, self.radius)
+
+    def view(self, k: int, seed=None):
+        """(image[H,W,4], (o[H,W,3], d[H,W,3], t[H,W,Nc])) of view k with fresh stratified jitter."""
+        o, d, t = self.gen(self.pose(k), seed=seed)
+        return analytic_rgba(o, d, self.white), (o, d, t)
+
+    def ray_batch(self, k: int, n_rays: int, offset: int = 0, seed=None):
+        """a contiguous window of n_rays rays of view k, shaped [1, n_rays/256, 256, .] for NeRF.compile"""
+        img, (o, d, t) = self.view(k, seed=seed)
+        total = self.wh * self.wh
+        assert n_rays <= total and n_rays % 256 == 0
+        off = offset % (total - n_rays + 1)
+        sl = slice(off, off + n_rays)
+        sh = (1, n_rays // 256, 256)
+        f = lambda x: x.reshape(total, -1)[sl].reshape(sh + (x.shape[-1],)).contiguous()  # noqa: E731
+        return f(img), (f(o), f(d), f(t))
