@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--ray-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the secondary 800x800 render metric")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -269,10 +270,11 @@ def main():
             "step_tflops": FLOP_TRAIN_PER_SAMPLE * (N_COARSE + N_COARSE + N_FINE) * RAYS_PER_GPU * world
             * args.steps / (ms * 1e-3) / 1e12,
             "losses": {"device_run": loss_dev, "e2e_last": {k: float(v) for k, v in logs.items()}}}
-    try:
-        line["render"] = render_ms_per_frame(precision, dev)
-    except Exception as e:  # the secondary metric must never take the headline down
-        line["render"] = {"error": str(e)[:200]}
+    if not args.no_render and world == 1:
+        try:
+            line["render"] = render_ms_per_frame(precision, dev)
+        except Exception as e:  # the secondary metric must never take the headline down
+            line["render"] = {"error": str(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"], _ = cpu_train_rays_per_sec()
     else:
