@@ -189,6 +189,12 @@ int knerf_adam_step(float* params, float* grads, float* m, float* v, int64_t n, 
 /* sum_c,rays (a-b)^2 / n  -> out[0] (device float); used for test_step losses / PSNR (nerf.py:306-330) */
 int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* Diagnostic: one tcgen05 tile, D[128,N] (fp32, row-major) = A[128,K] * B[N,K]^T from bf16 operand blobs in
+ * the library's chunk-major layout ([K/8][rows][8] for mode 0 = K-major; [rows/8][K][8] for mode 1 =
+ * MN-major, the weight-gradient form).  Pins the UMMA descriptor encoding in tests/test_gpu_tc.py.        */
+int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif
