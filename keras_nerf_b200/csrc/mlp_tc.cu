@@ -16,84 +16,33 @@
 // Shared memory: 2 x 64 KB hidden activations + 2 x 16 KB encodings + 4 x 16 KB weight stages = 224 KB.
 #include "mlp_tc.cuh"
 
-#include "tc_ptx.cuh"
+#include "tc_roles.cuh"
 
 namespace knerf {
 using namespace tc;
+using namespace tcl;
 
 namespace {
 
-constexpr int kTileM = 128;
-constexpr int kU = 256;
-constexpr int kKStage = 32;                       // K elements per weight stage
-constexpr int kStageBytes = kU * kKStage * 2;     // 16 KB (N = 256); N = 128 stages use half
-constexpr int kNumStages = 4;
-constexpr int kHSBytes = kTileM * kU * 2;         // 64 KB
-constexpr int kXSBytes = kTileM * 64 * 2;         // 16 KB
-constexpr int kChunkA = kTileM * 16;              // bytes between 8-element K chunks of an A operand (2048)
-constexpr int kFwdSteps = 10;
-constexpr int kThreads = 320;
-constexpr int kComputeThreads = 256;
-
-// ---- forward step table --------------------------------------------------------------------------------
-// step:        0    1..4   5      6,7   8          9
-// layer:       L0   L1-4   L5     L6,7  features   rgb_features      (sigma and rgb heads run on CUDA cores)
-__host__ __device__ constexpr int fwd_layer(int s) { return s < 8 ? s : (s == 8 ? 9 : 10); }
-__host__ __device__ constexpr int fwd_nk_h(int s) { return s == 0 ? 0 : 8; }          // K stages fed by HS
-__host__ __device__ constexpr int fwd_nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 9 ? 1 : 0); }
-__host__ __device__ constexpr int fwd_N(int s) { return s == 9 ? 128 : 256; }
-__host__ __device__ constexpr int fwd_stage_bytes(int s) { return fwd_N(s) * kKStage * 2; }
-__host__ __device__ constexpr int fwd_blob_off(int s) {
-  int off = 0;
-  for (int i = 0; i < s; ++i) off += (fwd_nk_h(i) + fwd_nk_x(i)) * fwd_stage_bytes(i);
-  return off;
-}
-constexpr int kFwdBlobBytes = fwd_blob_off(kFwdSteps);
-// fp32 side table appended to the blob (16-byte aligned copies; the Keras flat buffer is not: the 1-wide sigma
-// bias shifts everything after it): bias[l] at l*256 (l = 0..11), sigma kernel at 12*256, rgb kernel at 13*256
-constexpr int kAuxFloats = 12 * 256 + 256 + 512;
-constexpr int kAuxOff = kFwdBlobBytes;
-constexpr int kPackedBytes = kAuxOff + kAuxFloats * 4;   // + dgrad blob (added with the backward kernels)
-
-struct TcParams {
-  int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
-};
-
-// per-tile record of the activations the backward needs (training only), all in chunk-major bf16
-constexpr int kRecXS = 0;                          // PE(xyz)   [8 chunks][128][8]   16 KB
-constexpr int kRecDS = 16384;                      // PE(dir)   [8 chunks][128][8]   16 KB (chunks 4..7 zero)
-constexpr int kRecH0 = 32768;                      // h0..h7    8 x 64 KB
-constexpr int kRecF = kRecH0 + 8 * kHSBytes;       // features  64 KB
-constexpr int kRecG = kRecF + kHSBytes;            // rgb_features [16 chunks][128][8] 32 KB
-constexpr int kRecBytes = kRecG + 32768;           // 640 KB per 128 samples
-
-struct FwdSmem {
-  uint8_t hs[2][kHSBytes];
-  uint8_t xs[2][kXSBytes];
-  uint8_t stage[kNumStages][kStageBytes];
-  float part[kTileM][4];
-  uint64_t full[kNumStages], empty[kNumStages], a_ready[2], acc_ready[2];
-  uint32_t tmem_base;
-};
-
 // ---- weight packing --------------------------------------------------------------------------------------
-// forward blob: per step, per K stage: [4 chunks][N][8] with element (c, n, e) = W[row(ks, c, e)][n]
-__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ params, TcParams P,
-                                                       uint8_t* __restrict__ packed) {
-  const int total_vec = kFwdBlobBytes / 16;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += gridDim.x * blockDim.x) {
+// forward blob: per step, per K stage: [4 chunks][N][8], element (c, n, e) = W[row(ks, c, e)][n]   (W^T, K-major)
+// dgrad blob:   per step, per K stage: [4 chunks][256][8], element (c, n, e) = W[n][ks*32 + c*8 + e] (W, K-major)
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, TcParams P,
+                                                   uint8_t* __restrict__ packed) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (int v = gtid; v < kFwdBlobBytes / 16; v += gsz) {
     int byte = v * 16, s = 0;
-    while (s + 1 < kFwdSteps && byte >= fwd_blob_off(s + 1)) ++s;
-    const int local = byte - fwd_blob_off(s);
-    const int N = fwd_N(s), sb = fwd_stage_bytes(s);
+    while (s + 1 < FwdProg::kSteps && byte >= FwdProg::blob_off(s + 1)) ++s;
+    const int local = byte - FwdProg::blob_off(s);
+    const int N = FwdProg::N(s), sb = FwdProg::stage_bytes(s);
     const int ks = local / sb, r = local - ks * sb;
     const int c = r / (N * 16), n = (r - c * N * 16) / 16;
-    const int L = fwd_layer(s);
+    const int L = FwdProg::layer(s);
     const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : (L == 10) ? 283 : 256;
     const float* W = params + P.w_off[L];
     int row0;
-    if (ks < fwd_nk_h(s)) row0 = ks * kKStage + c * 8;
-    else row0 = (fwd_nk_h(s) > 0 ? 256 : 0) + (ks - fwd_nk_h(s)) * kKStage + c * 8;
+    if (ks < FwdProg::nk_h(s)) row0 = ks * kKStage + c * 8;
+    else row0 = (FwdProg::nk_h(s) > 0 ? 256 : 0) + (ks - FwdProg::nk_h(s)) * kKStage + c * 8;
     uint32_t w[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -104,8 +53,19 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
     }
     *reinterpret_cast<uint4*>(packed + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+  for (int v = gtid; v < kBwdBlobBytes / 16; v += gsz) {
+    const int byte = v * 16;
+    int b = 0;
+    while (b + 1 < BwdProg::kSteps && byte >= BwdProg::blob_off(b + 1)) ++b;
+    const int local = byte - BwdProg::blob_off(b);
+    const int ks = local / kStageBytes, r = local - ks * kStageBytes;
+    const int c = r / (256 * 16), n = (r - c * 256 * 16) / 16;
+    const float* W = params + P.w_off[BwdProg::layer(b)] + (int64_t)n * BwdProg::ld(b) + ks * kKStage + c * 8;
+    *reinterpret_cast<uint4*>(packed + kBwdBlobOff + byte) =
+        make_uint4(pack_bf16x2(W[0], W[1]), pack_bf16x2(W[2], W[3]), pack_bf16x2(W[4], W[5]), pack_bf16x2(W[6], W[7]));
+  }
   float* aux = reinterpret_cast<float*>(packed + kAuxOff);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kAuxFloats; i += gridDim.x * blockDim.x) {
+  for (int i = gtid; i < kAuxFloats; i += gsz) {
     const int blk = i >> 8, j = i & 255;
     float v = 0.f;
     if (blk < 12) {
@@ -194,87 +154,27 @@ __device__ __forceinline__ void copy_smem_to_global(const uint8_t* src, uint8_t*
 // ---- the fused forward kernel ----------------------------------------------------------------------------
 template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed,
-                  const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ t,
-                  int64_t M, int S, float4* __restrict__ rgbsigma, uint8_t* __restrict__ rec) {
+tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o, const float* __restrict__ d,
+                  const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
+                  uint8_t* __restrict__ rec) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
-
-  if (tid == 0) {
-    for (int i = 0; i < kNumStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.a_ready[i], kComputeThreads); mbar_init(&sm.acc_ready[i], 1); }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(&sm.tmem_base);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tmem = chain_setup(sm, tid, warp);
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int s = 0; s < kFwdSteps; ++s) {
-          const int nk = fwd_nk_h(s) + fwd_nk_x(s);
-          const uint32_t sb = fwd_stage_bytes(s);
-          const uint8_t* src = packed + fwd_blob_off(s);
-          for (int tl = 0; tl < 2; ++tl) {
-            for (int ks = 0; ks < nk; ++ks, ++it) {
-              const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1;
-              mbar_wait(&sm.empty[slot], ph ^ 1);
-              mbar_arrive_expect_tx(&sm.full[slot], sb);
-              tma_load_1d(sm.stage[slot], src + (size_t)ks * sb, sb, &sm.full[slot]);
-            }
-          }
-        }
-      }
-    }
+    if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
   } else if (warp == 1) {
-    // =========================== MMA issuer =============================
-    if (lane == 0) {
-      uint32_t it = 0, a_par[2] = {0, 0};
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int s = 0; s < kFwdSteps; ++s) {
-          const int nkh = fwd_nk_h(s), nk = nkh + fwd_nk_x(s);
-          const int N = fwd_N(s);
-          const uint32_t idesc = umma_idesc_bf16(kTileM, N, 0, 0);
-          const uint32_t chunk_b = (uint32_t)N * 16;
-          for (int tl = 0; tl < 2; ++tl) {
-            mbar_wait(&sm.a_ready[tl], a_par[tl]);
-            a_par[tl] ^= 1;
-            tc_fence_after();
-            const uint32_t d_tmem = tmem + tl * 256;
-            for (int ks = 0; ks < nk; ++ks, ++it) {
-              const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1;
-              mbar_wait(&sm.full[slot], ph);
-              tc_fence_after();
-              const uint32_t a_base = (ks < nkh) ? smem_u32(sm.hs[tl]) + ks * 4 * kChunkA
-                                                 : smem_u32(sm.xs[tl]) + (ks - nkh) * 4 * kChunkA;
-              const uint32_t b_base = smem_u32(sm.stage[slot]);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t da = umma_smem_desc(a_base + j * 2 * kChunkA, kChunkA, 128);
-                const uint64_t db = umma_smem_desc(b_base + j * 2 * chunk_b, chunk_b, 128);
-                umma_bf16(d_tmem, da, db, idesc, (ks > 0 || j > 0) ? 1u : 0u);
-              }
-              umma_commit(&sm.empty[slot]);
-            }
-            umma_commit(&sm.acc_ready[tl]);
-          }
-        }
-      }
-    }
+    if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
   } else {
     // =========================== compute warps ==========================
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ctid = tid - 64;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
     float sig_keep[2] = {0.f, 0.f};
 
@@ -295,10 +195,8 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed,
       prologue(blockIdx.x, 1);
     }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      for (int s = 0; s < kFwdSteps; ++s) {
-        const int L = fwd_layer(s);
-        const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
-        const float* bias = aux + L * 256;
+      for (int s = 0; s < FwdProg::kSteps; ++s) {
+        const float* bias = aux + FwdProg::layer(s) * 256;
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = pair * 2 + tl;
@@ -412,9 +310,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed,
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  chain_teardown(tmem, warp);
 }
 
 }  // namespace
@@ -426,10 +322,10 @@ int64_t tc_packed_weight_bytes(const Model& m) { return is_flagship(m) ? kPacked
 int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training) {
   if (!is_flagship(m)) return -1;
   if (!training) return 256;
-  return cdiv(rows, kTileM) * (int64_t)kRecBytes + 256;
+  return cdiv(rows, kTileM) * (int64_t)(kRecBytes + kDzBytes) + 256;
 }
 
-static TcParams make_params(const Model& m) {
+TcParams tc_make_params(const Model& m) {
   TcParams P;
   for (int i = 0; i < 12; ++i) { P.w_off[i] = m.L[i].w_off; P.b_off[i] = m.L[i].b_off; }
   return P;
@@ -437,40 +333,37 @@ static TcParams make_params(const Model& m) {
 
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st) {
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
-  pack_fwd_kernel<<<kNumSMs, 256, 0, st>>>(params, make_params(m), (uint8_t*)packed);
+  KN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_weights: packed must be 16-byte aligned");
+  pack_kernel<<<kNumSMs * 2, 256, 0, st>>>(params, tc_make_params(m), (uint8_t*)packed);
   KN_LAUNCH_CHECK();
   return KNERF_OK;
 }
 
 int tc_forward(const Model& m, const float* params, const void* packed, const float* o, const float* d, const float* t,
                int64_t R, int S, bool training, float* rgbsigma, char* ws, int64_t ws_bytes, cudaStream_t st) {
+  (void)params;
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
   const int64_t M = R * S;
   if (training && ws_bytes < tc_workspace_bytes(m, M, true))
     return fail(KNERF_ERR_WORKSPACE, "tc_forward: workspace %lld < %lld bytes", (long long)ws_bytes,
                 (long long)tc_workspace_bytes(m, M, true));
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(params) & 15) == 0,
-               "tc_forward: rgbsigma / packed / params must be 16-byte aligned");
+                   (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+               "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");
   const int64_t n_pairs = cdiv(cdiv(M, kTileM), 2);
   const int grid = (int)std::min<int64_t>(n_pairs, kNumSMs);
-  const size_t smem = sizeof(FwdSmem);
+  const size_t smem = sizeof(ChainSmem);
   if (training) {
     KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mlp_fwd_kernel<true><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S,
-                                                          (float4*)rgbsigma, (uint8_t*)ws);
+    tc_mlp_fwd_kernel<true><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S, (float4*)rgbsigma,
+                                                          (uint8_t*)ws);
   } else {
     KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mlp_fwd_kernel<false><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S,
-                                                           (float4*)rgbsigma, nullptr);
+    tc_mlp_fwd_kernel<false><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S, (float4*)rgbsigma,
+                                                           nullptr);
   }
   KN_LAUNCH_CHECK();
   return KNERF_OK;
-}
-
-int tc_backward(const Model&, const float*, const void*, const float*, int64_t, int, float*, char*, int64_t,
-                cudaStream_t) {
-  return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 backward not built yet");
 }
 
 }  // namespace knerf

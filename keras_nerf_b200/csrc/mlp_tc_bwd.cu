@@ -1,0 +1,415 @@
+// a11 (KNERF_BF16 mode): backward of the NeRF MLP on tcgen05 tensor cores.
+//
+//  1. tc_mlp_dgrad_kernel -- the forward's chain structure run backwards: starting from the gradient w.r.t. the
+//     head pre-activations (from the fused compositing backward) it walks rgb_features -> features/sigma ->
+//     layer 7 .. layer 1, each step one [128 x 256] x [256 x 256] tcgen05 GEMM against W^T followed by a
+//     ReLU-mask epilogue (mask = saved forward activation > 0).  Every pre-activation gradient tile dZ_l is
+//     written once to HBM in chunk-major bf16 for step 2; bias gradients are the column sums of the same tiles.
+//     No gradient flows into the xyz / direction encodings (mlp.py inputs are constants: nerf.py:361-369).
+//  2. tc_wgrad_kernel -- dW_l = X_l^T dZ_l with the reduction over SAMPLES: the saved activation / gradient
+//     blobs are consumed as MN-major UMMA operands (same bytes, other axis; see tc_ptx.cuh), fp32 partial
+//     sums stay in TMEM across all tiles of a work item and are flushed once with red.global.add.f32.
+#include "mlp_tc.cuh"
+#include "tc_roles.cuh"
+
+namespace knerf {
+using namespace tc;
+using namespace tcl;
+
+TcParams tc_make_params(const Model& m);
+
+namespace {
+
+// =============================================================================================================
+// dgrad chain
+// =============================================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict__ d_pre, int64_t M,
+                    const uint8_t* __restrict__ rec, uint8_t* __restrict__ dz, float* __restrict__ grads, TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const uint32_t tmem = chain_setup(sm, tid, warp);
+
+  if (warp == 0) {
+    if (lane == 0) producer_role<BwdProg>(sm, packed + kBwdBlobOff, n_pairs);
+  } else if (warp == 1) {
+    if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
+  } else {
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int ctid = tid - 64;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
+    const float* wsig = aux + 12 * 256;
+    const float* wrgb = aux + 13 * 256;
+    uint32_t acc_par[2] = {0, 0};
+    float dsig_keep[2] = {0.f, 0.f};
+
+    // tile start: dG = d(rgb_pre) Wc^T (K = 3, CUDA cores) becomes the first A operand
+    auto prologue = [&](int64_t pair, int tl) {
+      const int64_t tile = pair * 2 + tl;
+      const int64_t g = tile * kTileM + r;
+      const bool active = tile < n_tiles;
+      float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < M) dp = d_pre[g];
+      dsig_keep[tl] = dp.w;
+      uint8_t* dz_t = dz + tile * kDzBytes;
+      if (active) {
+        const uint4 pk = (h == 0) ? make_uint4(pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dz_t + kDzP + h * kChunkA + r * 16) = pk;
+      }
+      if (h == 0) {   // bias gradients of the two heads: db_rgb = sum d(rgb_pre), db_sigma = sum d(sigma_pre)
+        const float s0 = warp_sum(dp.x), s1 = warp_sum(dp.y), s2 = warp_sum(dp.z), s3 = warp_sum(dp.w);
+        if (lane == 0) {
+          atomicAdd(grads + P.b_off[11], s0); atomicAdd(grads + P.b_off[11] + 1, s1);
+          atomicAdd(grads + P.b_off[11] + 2, s2); atomicAdd(grads + P.b_off[8], s3);
+        }
+      }
+#pragma unroll 2
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const int col = h * 64 + c8 * 8;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float* wr = wrgb + (col + e) * 3;
+          x[e] = dp.x * __ldg(wr) + dp.y * __ldg(wr + 1) + dp.z * __ldg(wr + 2);
+        }
+        const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                    pack_bf16x2(x[6], x[7]));
+        const int off = (col >> 3) * kChunkA + r * 16;
+        *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
+        if (active) *reinterpret_cast<uint4*>(dz_t + kDzG + off) = pk;
+      }
+      fence_async_smem();
+      mbar_arrive(&sm.a_ready[tl]);
+      named_bar_sync(1, kComputeThreads);
+      colsum_to_global(sm.hs[tl], 128, grads + P.b_off[10], ctid);     // db of rgb_features
+    };
+
+    if ((int64_t)blockIdx.x < n_pairs) {
+      prologue(blockIdx.x, 0);
+      prologue(blockIdx.x, 1);
+    }
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int b = 0; b < BwdProg::kSteps; ++b) {
+        const int zi = 8 - b;                                  // index of the dZ this step produces (b >= 1)
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+          const int64_t tile = pair * 2 + tl;
+          const bool active = tile < n_tiles;
+          uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
+          const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
+          float* db = grads + (b == 0 ? P.b_off[9] : P.b_off[zi]);
+          const float dsig = dsig_keep[tl];
+          mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
+          acc_par[tl] ^= 1;
+          tc_fence_after();
+#pragma unroll 1
+          for (int gI = 0; gI < 4; ++gI) {
+            const int col0 = h * 128 + gI * 32;
+            float v[32];
+            tmem_ld32(tmem + lane_base + tl * 256 + col0, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const int col = col0 + c8 * 8;
+              const int off = (col >> 3) * kChunkA + r * 16;
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = v[c8 * 8 + e];
+              if (b == 1) {   // + d(sigma_pre) Ws^T: the sigma head shares h7 with `features`
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + col));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + col + 4));
+                x[0] += dsig * w0.x; x[1] += dsig * w0.y; x[2] += dsig * w0.z; x[3] += dsig * w0.w;
+                x[4] += dsig * w1.x; x[5] += dsig * w1.y; x[6] += dsig * w1.z; x[7] += dsig * w1.w;
+              }
+              if (b >= 1) {   // ReLU': pass where the saved forward activation is > 0
+                uint4 hm = make_uint4(0u, 0u, 0u, 0u);
+                if (active) hm = __ldg(reinterpret_cast<const uint4*>(mask + off));
+                x[0] = bf16_lo(hm.x) > 0.f ? x[0] : 0.f; x[1] = bf16_hi(hm.x) > 0.f ? x[1] : 0.f;
+                x[2] = bf16_lo(hm.y) > 0.f ? x[2] : 0.f; x[3] = bf16_hi(hm.y) > 0.f ? x[3] : 0.f;
+                x[4] = bf16_lo(hm.z) > 0.f ? x[4] : 0.f; x[5] = bf16_hi(hm.z) > 0.f ? x[5] : 0.f;
+                x[6] = bf16_lo(hm.w) > 0.f ? x[6] : 0.f; x[7] = bf16_hi(hm.w) > 0.f ? x[7] : 0.f;
+              }
+              const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                          pack_bf16x2(x[6], x[7]));
+              *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
+              if (active) *reinterpret_cast<uint4*>(out + off) = pk;
+            }
+          }
+          tc_fence_before();
+          fence_async_smem();
+          if (b + 1 < BwdProg::kSteps) mbar_arrive(&sm.a_ready[tl]);
+          named_bar_sync(1, kComputeThreads);
+          colsum_to_global(sm.hs[tl], 256, db, ctid);
+          if (b + 1 == BwdProg::kSteps) {
+            const int64_t next = pair + gridDim.x;
+            if (next < n_pairs) {
+              named_bar_sync(1, kComputeThreads);   // everyone is done reading hs[tl] before it is rebuilt
+              prologue(next, tl);
+            }
+          }
+        }
+      }
+    }
+  }
+  chain_teardown(tmem, warp);
+}
+
+// =============================================================================================================
+// weight gradients
+// =============================================================================================================
+constexpr int kWUnitBytes = 32768;     // 16 chunks x 128 samples x 16 B: 128 features (A) or 128 outputs (B)
+constexpr int kWSlots = 6;
+constexpr int kWThreads = 192;         // warp 0 producer, warp 1 MMA, warps 2-5 flush
+constexpr int kNumTasks = 13;
+
+struct WUnit { int src, off, bytes; };                       // src 0 = forward record, 1 = dz record
+struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b; };
+struct WTask { int n_units; WUnit u[4]; int n_groups; WGroup g[4]; int cost; };
+// mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
+
+struct WTaskTable { WTask t[kNumTasks]; };
+
+static WTaskTable build_task_table() {
+  WTaskTable T{};
+  int n = 0;
+  auto big = [&](int layer, int a_off, int b_off, int row_base) {   // A: two 128-feature halves, B: two 128-output halves
+    WTask& t = T.t[n++];
+    t.n_units = 4;
+    t.u[0] = {0, a_off, kWUnitBytes}; t.u[1] = {1, b_off, kWUnitBytes};
+    t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes}; t.u[3] = {0, a_off + kWUnitBytes, kWUnitBytes};
+    t.n_groups = 4;
+    t.g[0] = {0, 1, 0, 128, layer, row_base, 128, 0, 0, 0, 0};
+    t.g[1] = {0, 2, 128, 128, layer, row_base, 128, 128, 0, 1, 0};
+    t.g[2] = {3, 1, 256, 128, layer, row_base + 128, 128, 0, 0, 0, 1};
+    t.g[3] = {3, 2, 384, 128, layer, row_base + 128, 128, 128, 0, 1, 1};
+    t.cost = 128;
+  };
+  auto xpart = [&](int layer, int b_off, int row_base) {           // A: PE(xyz) (63 valid rows), B: two halves
+    WTask& t = T.t[n++];
+    t.n_units = 3;
+    t.u[0] = {0, kRecXS, kWUnitBytes}; t.u[1] = {1, b_off, kWUnitBytes}; t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes};
+    t.n_groups = 2;
+    t.g[0] = {0, 1, 0, 128, layer, row_base, 63, 0, 0, 0, 1};
+    t.g[1] = {0, 2, 128, 128, layer, row_base, 63, 128, 0, 1, 1};
+    t.cost = 96;
+  };
+  xpart(0, kDzZ0, 0);                                                        // layer 0
+  for (int l = 1; l <= 7; ++l) big(l, kRecH0 + (l - 1) * kHSBytes, kDzZ0 + l * kHSBytes, 0);   // layers 1..7 (h part)
+  xpart(5, kDzZ0 + 5 * kHSBytes, 256);                                       // layer 5, skip rows 256..318
+  big(9, kRecH0 + 7 * kHSBytes, kDzF, 0);                                    // features
+  {  // sigma (A = h7 halves) and rgb (A = rgb_features) against the packed d_pre operand (N = 16)
+    WTask& t = T.t[n++];
+    t.n_units = 4;
+    t.u[0] = {1, kDzP, 4096}; t.u[1] = {0, kRecH0 + 7 * kHSBytes, kWUnitBytes};
+    t.u[2] = {0, kRecH0 + 7 * kHSBytes + kWUnitBytes, kWUnitBytes}; t.u[3] = {0, kRecG, kWUnitBytes};
+    t.n_groups = 3;
+    t.g[0] = {1, 0, 0, 16, 8, 0, 128, 0, 1, 1, 0};
+    t.g[1] = {2, 0, 32, 16, 8, 128, 128, 0, 1, 1, 0};
+    t.g[2] = {3, 0, 64, 16, 11, 0, 128, 0, 2, 1, 1};
+    t.cost = 100;
+  }
+  {  // rgb_features: A = features halves + PE(dir) (27 valid rows), B = dG (N = 128)
+    WTask& t = T.t[n++];
+    t.n_units = 4;
+    t.u[0] = {1, kDzG, kWUnitBytes}; t.u[1] = {0, kRecF, kWUnitBytes}; t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes};
+    t.u[3] = {0, kRecDS, kWUnitBytes};
+    t.n_groups = 3;
+    t.g[0] = {1, 0, 0, 128, 10, 0, 128, 0, 0, 1, 0};
+    t.g[1] = {2, 0, 128, 128, 10, 128, 128, 0, 0, 1, 0};
+    t.g[2] = {3, 0, 256, 128, 10, 256, 27, 0, 0, 1, 1};
+    t.cost = 128;
+  }
+  return T;
+}
+
+struct WSmem {
+  uint8_t slot[kWSlots][kWUnitBytes];
+  uint64_t full[kWSlots], empty[kWSlots], acc_done, acc_free;
+  uint32_t tmem_base;
+};
+
+struct WItem { int task; int64_t tile_lo, tile_hi; };
+
+__device__ __forceinline__ WItem decode_item(const WTaskTable& T, int item, int slabs_per_cost_x128, int64_t n_tiles) {
+  // item ids are laid out task after task; task k owns max(1, cost_k * slabs / 128) slabs
+  WItem it{-1, 0, 0};
+  int base = 0;
+  for (int k = 0; k < kNumTasks; ++k) {
+    const int ns = max(1, T.t[k].cost * slabs_per_cost_x128 / 128);
+    if (item < base + ns) {
+      const int s = item - base;
+      it.task = k;
+      it.tile_lo = n_tiles * s / ns;
+      it.tile_hi = n_tiles * (s + 1) / ns;
+      return it;
+    }
+    base += ns;
+  }
+  return it;
+}
+
+static int count_items(const WTaskTable& T, int slabs_per_cost_x128) {
+  int n = 0;
+  for (int k = 0; k < kNumTasks; ++k) n += std::max(1, T.t[k].cost * slabs_per_cost_x128 / 128);
+  return n;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1)
+tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz, int64_t n_tiles,
+                float* __restrict__ grads, TcParams P, const __grid_constant__ WTaskTable T, int n_items,
+                int slabs) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    mbar_init(&sm.acc_done, 1);
+    mbar_init(&sm.acc_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&sm.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WItem w = decode_item(T, item, slabs, n_tiles);
+        const WTask& t = T.t[w.task];
+        for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile) {
+          for (int k = 0; k < t.n_units; ++k, ++it) {
+            const uint32_t slot = it % kWSlots, ph = (it / kWSlots) & 1;
+            const uint8_t* src = (t.u[k].src == 0 ? rec + tile * kRecBytes : dz + tile * kDzBytes) + t.u[k].off;
+            mbar_wait(&sm.empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&sm.full[slot], t.u[k].bytes);
+            tma_load_1d(sm.slot[slot], src, t.u[k].bytes, &sm.full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, free_par = 0;
+      bool first_item = true;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WItem w = decode_item(T, item, slabs, n_tiles);
+        const WTask& t = T.t[w.task];
+        if (w.tile_lo >= w.tile_hi) continue;
+        if (!first_item) {   // the previous item's accumulators must have been flushed
+          mbar_wait(&sm.acc_free, free_par);
+          free_par ^= 1;
+          tc_fence_after();
+        }
+        first_item = false;
+        for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile, it += t.n_units) {
+          for (int gi = 0; gi < t.n_groups; ++gi) {
+            const WGroup& g = t.g[gi];
+            const uint32_t ia = it + g.a, ib = it + g.b;
+            const uint32_t sa = ia % kWSlots, sb = ib % kWSlots;
+            mbar_wait(&sm.full[sa], (ia / kWSlots) & 1);
+            mbar_wait(&sm.full[sb], (ib / kWSlots) & 1);
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(128, g.N, 1, 1);
+            const uint32_t a_base = smem_u32(sm.slot[sa]), b_base = smem_u32(sm.slot[sb]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // K = 128 samples per tile, 16 per MMA; MN-major: LBO = 128 B, SBO = 2 KB
+              const uint64_t da = umma_smem_desc(a_base + k * 256, 128, kChunkA);
+              const uint64_t db = umma_smem_desc(b_base + k * 256, 128, kChunkA);
+              umma_bf16(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
+            }
+            if (g.free_a) umma_commit(&sm.empty[sa]);
+            if (g.free_b) umma_commit(&sm.empty[sb]);
+          }
+        }
+        umma_commit(&sm.acc_done);
+      }
+    }
+  } else {
+    // flush warps: TMEM lane quadrant = warp & 3
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t done_par = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WItem w = decode_item(T, item, slabs, n_tiles);
+      const WTask& t = T.t[w.task];
+      if (w.tile_lo >= w.tile_hi) continue;
+      mbar_wait(&sm.acc_done, done_par);
+      done_par ^= 1;
+      tc_fence_after();
+      for (int gi = 0; gi < t.n_groups; ++gi) {
+        const WGroup& g = t.g[gi];
+        const int ncol = g.N < 32 ? 32 : g.N;
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem + lane_base + g.col + c0, v);   // warp-collective: outside the row guard
+          if (row < g.row_limit) {
+            if (g.mode == 0) {
+              const int ld = (g.layer == 10) ? 128 : 256;
+              float* dst = grads + P.w_off[g.layer] + (int64_t)(g.row_base + row) * ld + g.col_base + c0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+            } else if (g.mode == 1) {
+              atomicAdd(grads + P.w_off[8] + g.row_base + row, v[3]);
+            } else {
+              float* dst = grads + P.w_off[11] + row * 3;
+              atomicAdd(dst, v[0]); atomicAdd(dst + 1, v[1]); atomicAdd(dst + 2, v[2]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.acc_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
+                float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
+  (void)params;
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
+  KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
+  const int64_t M = R * S;
+  if (ws_bytes < tc_workspace_bytes(m, M, true))
+    return fail(KNERF_ERR_WORKSPACE, "tc_backward: workspace %lld < %lld bytes", (long long)ws_bytes,
+                (long long)tc_workspace_bytes(m, M, true));
+  KN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_pre) & 15) == 0, "tc_backward: d_pre must be 16-byte aligned");
+  const int64_t n_tiles = cdiv(M, kTileM);
+  uint8_t* rec = (uint8_t*)ws;
+  uint8_t* dz = rec + n_tiles * (int64_t)kRecBytes;
+  const TcParams P = tc_make_params(m);
+
+  {
+    const int64_t n_pairs = cdiv(n_tiles, 2);
+    const int grid = (int)std::min<int64_t>(n_pairs, kNumSMs);
+    const size_t smem = sizeof(ChainSmem);
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_mlp_dgrad_kernel<<<grid, kThreads, smem, st>>>((const uint8_t*)packed, (const float4*)d_pre, M, rec, dz, grads, P);
+    KN_LAUNCH_CHECK();
+  }
+  {
+    static const WTaskTable h_table = build_task_table();   // ~3 KB, passed by value as a __grid_constant__
+    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(26, n_tiles / 4));
+    const int n_items = count_items(h_table, slabs);
+    const int grid = std::min(n_items, kNumSMs);
+    const size_t smem = sizeof(WSmem);
+    KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, P, h_table, n_items, slabs);
+    KN_LAUNCH_CHECK();
+  }
+  return KNERF_OK;
+}
+
+}  // namespace knerf

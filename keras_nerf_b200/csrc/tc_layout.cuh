@@ -1,0 +1,93 @@
+// Shapes, step tables and HBM layouts shared by the tcgen05 forward (mlp_tc.cu) and backward
+// (mlp_tc_bwd.cu) kernels.  Flagship model only: 8 x 256, skip 4, L = 10 / 4.
+#pragma once
+
+#include <stdint.h>
+
+namespace knerf {
+namespace tcl {
+
+constexpr int kTileM = 128;                        // samples per tile (UMMA M)
+constexpr int kU = 256;
+constexpr int kKStage = 32;                        // K elements per weight stage
+constexpr int kStageBytes = kU * kKStage * 2;      // 16 KB (N = 256); N = 128 stages use half
+constexpr int kNumStages = 4;
+constexpr int kHSBytes = kTileM * kU * 2;          // 64 KB: one [128 x 256] bf16 operand, chunk-major
+constexpr int kXSBytes = kTileM * 64 * 2;          // 16 KB
+constexpr int kChunkA = kTileM * 16;               // bytes between 8-element chunks of a 128-row operand (2048)
+constexpr int kThreads = 320;
+constexpr int kComputeThreads = 256;
+
+// ---- forward steps ---------------------------------------------------------------------------------------
+// step:        0    1..4   5      6,7   8          9
+// layer:       L0   L1-4   L5     L6,7  features   rgb_features      (sigma and rgb heads run on CUDA cores)
+struct FwdProg {
+  static constexpr int kSteps = 10;
+  __host__ __device__ static constexpr int layer(int s) { return s < 8 ? s : (s == 8 ? 9 : 10); }
+  __host__ __device__ static constexpr int nk_h(int s) { return s == 0 ? 0 : 8; }   // K stages fed by hs
+  __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 9 ? 1 : 0); }
+  __host__ __device__ static constexpr int N(int s) { return s == 9 ? 128 : 256; }
+  __host__ __device__ static constexpr int stage_bytes(int s) { return N(s) * kKStage * 2; }
+  __host__ __device__ static constexpr int blob_off(int s) {
+    int off = 0;
+    for (int i = 0; i < s; ++i) off += (nk_h(i) + nk_x(i)) * stage_bytes(i);
+    return off;
+  }
+};
+constexpr int kFwdBlobBytes = FwdProg::blob_off(FwdProg::kSteps);
+
+// ---- backward (dgrad) steps --------------------------------------------------------------------------------
+// step b:      0               1                2 .. 8
+// computes:    dF = dG Wg^T    dZ7 = (dF Wf^T + dsigma Ws^T) * [h7>0]      dZ_{8-b} = (dZ_{9-b} W_{9-b}^T) * [h_{8-b}>0]
+// weights:     rgb_features    features         layer 7 .. layer 1        (rows < 256 of the Keras [in,out] kernel)
+struct BwdProg {
+  static constexpr int kSteps = 9;
+  __host__ __device__ static constexpr int layer(int b) { return b == 0 ? 10 : (b == 1 ? 9 : 9 - b); }
+  __host__ __device__ static constexpr int nk_h(int b) { return b == 0 ? 4 : 8; }
+  __host__ __device__ static constexpr int nk_x(int) { return 0; }
+  __host__ __device__ static constexpr int N(int) { return 256; }
+  __host__ __device__ static constexpr int stage_bytes(int) { return kStageBytes; }
+  __host__ __device__ static constexpr int blob_off(int b) { return (b == 0 ? 0 : 4 + (b - 1) * 8) * kStageBytes; }
+  __host__ __device__ static constexpr int ld(int b) { return b == 0 ? 128 : 256; }       // fan_out of that kernel
+};
+constexpr int kBwdBlobBytes = BwdProg::blob_off(BwdProg::kSteps);
+
+// ---- packed weight buffer ------------------------------------------------------------------------------------
+// [forward blob][dgrad blob][fp32 side table].  The side table holds 16-byte aligned copies (the Keras flat
+// buffer is not aligned: the 1-wide sigma bias shifts everything after it): bias[l] at l*256 (l = 0..11),
+// sigma kernel [256] at 12*256, rgb kernel [128,3] at 13*256.
+constexpr int kBwdBlobOff = kFwdBlobBytes;
+constexpr int kAuxOff = kBwdBlobOff + kBwdBlobBytes;
+constexpr int kAuxFloats = 12 * 256 + 256 + 512;
+constexpr int kPackedBytes = kAuxOff + kAuxFloats * 4;
+
+struct TcParams {
+  int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
+};
+
+// ---- per-tile records in the training workspace (chunk-major bf16) -------------------------------------------
+// activations saved by the forward:
+constexpr int kRecXS = 0;                          // PE(xyz)      [8 chunks][128][8]   16 KB
+constexpr int kRecDS = 16384;                      // PE(dir)      [8 chunks][128][8]   16 KB (chunks 4..7 zero)
+constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
+constexpr int kRecF = kRecH0 + 8 * kHSBytes;       // features     64 KB
+constexpr int kRecG = kRecF + kHSBytes;            // rgb_features [16 chunks][128][8]  32 KB
+constexpr int kRecBytes = kRecG + 32768;           // 640 KB per 128 samples
+// pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
+constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB
+constexpr int kDzF = 8 * kHSBytes;                 // d features   64 KB
+constexpr int kDzG = kDzF + kHSBytes;              // d rgb_features 32 KB
+constexpr int kDzP = kDzG + 32768;                 // (d rgb_pre[3], d sigma_pre, 0...) [2 chunks][128][8]  4 KB
+constexpr int kDzBytes = kDzP + 4096;              // 612 KB per 128 samples
+
+struct ChainSmem {
+  uint8_t hs[2][kHSBytes];
+  uint8_t xs[2][kXSBytes];
+  uint8_t stage[kNumStages][kStageBytes];
+  float part[kTileM][4];
+  uint64_t full[kNumStages], empty[kNumStages], a_ready[2], acc_ready[2];
+  uint32_t tmem_base;
+};
+
+}  // namespace tcl
+}  // namespace knerf
