@@ -35,3 +35,171 @@ def test_umma_selftest(mode, N, K):
     ref = A.float() @ B.float().T
     err = float((out.cpu() - ref).abs().max())
     assert err <= 1e-3 * max(1.0, float(ref.abs().max())), err
+
+
+# ---- fused bf16 MLP kernels ----------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+import oracle as O  # noqa: E402
+from conftest import load_golden  # noqa: E402
+
+
+def _models(R, training=True):
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    out = []
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True, is_training=training)
+        out.append(m)
+    assert torch.equal(out[0].fine.params, out[1].fine.params)
+    return out
+
+
+def _rays(R, S, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.zeros(R, 3)
+    o[:, 2] = 4.0
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0, 0, -1.0]), dim=-1)
+    t = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, dim=-1).values.contiguous()
+    tgt = torch.rand(R, 3, generator=g)
+    dev = torch.device("cuda")
+    return o.to(dev), d.to(dev), t.to(dev), tgt.to(dev)
+
+
+def _fwd(m, net, o, d, t, training):
+    from keras_nerf_b200 import _lib
+    R, S = t.shape
+    out = torch.full((R, S, 4), float("nan"), device=t.device)
+    _lib.call("knerf_mlp_forward", C.byref(m.cfg), _lib.ptr(net.params), m._packed_ptr("fine" if net is m.fine else "coarse"),
+              _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R, S, m._prec, int(training), _lib.ptr(out), m._ws.data_ptr(),
+              m._ws.numel(), _lib.stream())
+    return out
+
+
+def _composite(rgbs, t):
+    from keras_nerf_b200 import _lib
+    R, S = t.shape
+    img = torch.empty(R, 3, device=t.device)
+    _lib.call("knerf_composite_forward", _lib.ptr(rgbs), None, None, _lib.ptr(t), R, S, 1, 1, 1e-10, _lib.ptr(img), None,
+              None, None, _lib.stream())
+    return img
+
+
+@pytest.mark.parametrize("R,S", [(512, 192), (37, 192), (2, 64), (5, 64), (300, 320)])
+def test_tc_forward_vs_fp32(R, S):
+    """north star: a bf16 MLP mode agrees within max-abs 2e-3 per pixel and 0.05 dB PSNR (R*S not a multiple of
+    the 256-sample tile pair exercises the padding path)"""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    ms = []
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec, n_coarse=64, n_fine=S - 64 if S > 64 else 128)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True, is_training=False)
+        ms.append(m)
+    m32, m16 = ms
+    o, d, t, tgt = _rays(R, S, seed=R)
+    a = _fwd(m32, m32.fine, o, d, t, False)
+    b = _fwd(m16, m16.fine, o, d, t, False)
+    assert not torch.isnan(b).any()
+    assert float((a[..., :3] - b[..., :3]).abs().max()) <= 5e-3          # per-sample rgb
+    assert float((a[..., 3] - b[..., 3]).abs().max()) <= 1e-2            # per-sample sigma
+    ia, ib = _composite(a, t), _composite(b, t)
+    assert float((ia - ib).abs().max()) <= 2e-3                          # per pixel (north star)
+    psnr = lambda x: float(-10 * torch.log10(((x - tgt) ** 2).mean()))  # noqa: E731
+    assert abs(psnr(ia) - psnr(ib)) <= 0.05
+
+
+def test_tc_render_golden_model():
+    """whole coarse+fine render in bf16 mode against the fixture produced by the reference's own code"""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    g = load_golden("model")
+    mlp_mod.set_seed(int(g["init_seed"]))
+    H, W = int(g["H"]), int(g["W"])
+    m = K.NeRF(precision="bf16", scan_mode="sequential")
+    m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=H, image_width=W, ray_chunks=256,
+              white_background=True, is_training=False)
+    c, f = m.predict_and_render_images((g["o"][None], g["d"][None], g["t"][None]), u_fine=g["u_fine"])
+    assert float((c["image"].cpu() - torch.from_numpy(g["image_coarse"])).abs().max()) <= 2e-3
+    assert float((c["weights"].cpu() - torch.from_numpy(g["weights_coarse"])).abs().max()) <= 2e-3
+    # fine pass end to end: loose (ill-conditioned sampler quirk, see test_gpu_parity.py::test_model_render_golden)
+    mse = float(((f["image"].cpu() - torch.from_numpy(g["image_fine"])) ** 2).mean())
+    assert -10 * np.log10(mse) > 45.0
+
+
+@pytest.mark.parametrize("R,S", [(512, 192), (37, 192), (3, 64)])
+def test_tc_backward_vs_fp32(R, S):
+    from keras_nerf_b200 import _lib
+    m32, m16 = _models(R)
+    o, d, t, tgt = _rays(R, S, seed=7 + R)
+    grads = {}
+    for m in (m32, m16):
+        out = _fwd(m, m.fine, o, d, t, True)
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        for _ in range(2):   # gradients ACCUMULATE: two calls give exactly twice the gradient
+            _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                      R, S, m._prec, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        grads[m.precision] = gbuf.cpu() / 2
+    a, b = grads["fp32"], grads["bf16"]
+    assert torch.isfinite(b).all()
+    # bf16 rounding noise is independent per sample and averages out as 1/sqrt(samples) (measured: layer_0 kernel
+    # 1.6e-2 at 98k samples, 5.5e-2 at 7k): scale the bound accordingly; the sharp check of the ragged-tile
+    # handling is test_tc_backward_padding_exact below.
+    tol = 4e-2 * max(1.0, (512 * 192 / (R * S)) ** 0.5)
+    off = 0
+    for name, fi, fo in O.layer_shapes(O.NerfConfig()):
+        for n in (fi * fo, fo):
+            x, y = a[off:off + n], b[off:off + n]
+            assert float((x - y).norm() / x.norm()) <= tol, name
+            off += n
+
+
+def test_tc_backward_padding_exact():
+    """37 rays x 192 samples = 55.5 tiles.  The same 37 rays embedded in a 64-ray call whose other rows get a zero
+    upstream gradient must give the same weight gradients: rows outside the problem contribute exactly nothing."""
+    from keras_nerf_b200 import _lib
+    _, m = _models(64)
+    S = 192
+    o, d, t, tgt = _rays(64, S, seed=11)
+    res = []
+    for R in (37, 64):
+        out = _fwd(m, m.fine, o[:R].contiguous(), d[:R].contiguous(), t[:R].contiguous(), True)
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t[:R].contiguous()), R, S, 1, 1, 1e-10, None,
+                  _lib.ptr(tgt[:R].contiguous()), 2.0 / (3 * 37), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        dpre[37:] = 0
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre), R, S,
+                  m._prec, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        res.append(gbuf.cpu())
+    scale = float(res[1].abs().max())
+    assert scale > 0 and float((res[0] - res[1]).abs().max()) <= 1e-5 * scale   # fp32 atomics order only
+
+
+def test_tc_train_step_tracks_fp32():
+    """three optimizer steps in bf16 mode stay close to the fp32 mode (same draws)"""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    g = load_golden("model")
+    H, W = int(g["H"]), int(g["W"])
+    rays = (g["o"][None], g["d"][None], g["t"][None])
+    logs = {}
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec, scan_mode="sequential")
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=H, image_width=W, ray_chunks=128,
+                  white_background=True)
+        logs[prec] = [m.train_step((g["images"], rays), u_fine=g["u_fine"]) for _ in range(3)]
+    for a, b in zip(logs["fp32"], logs["bf16"]):
+        assert b["coarse_loss"] == pytest.approx(a["coarse_loss"], rel=2e-2)
+        assert b["fine_loss"] == pytest.approx(a["fine_loss"], rel=2e-2)
+        assert b["coarse_psnr"] == pytest.approx(a["coarse_psnr"], abs=0.1)
+    assert logs["bf16"][2]["coarse_loss"] < logs["bf16"][0]["coarse_loss"]
