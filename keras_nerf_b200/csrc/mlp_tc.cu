@@ -204,6 +204,15 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           const bool valid = g < M;
           const bool save = TRAIN && tile < n_tiles;
           uint8_t* rec_t = rec + tile * kRecBytes;
+          // software pipeline against load latency (the epilogue is the critical path): the bias vectors of a
+          // 32-column group are fetched before the accumulator is waited for / while the previous group's
+          // TMEM load is in flight
+          float4 bnext[8];
+          {
+            const float4* bp = reinterpret_cast<const float4*>(bias + (s < 9 ? h * 128 : h * 64));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
+          }
           mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
@@ -213,21 +222,29 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             uint8_t* rec_out = rec_t + (s < 8 ? kRecH0 + s * kHSBytes : kRecF);
             float sigdot = 0.f;
             const float* wsig = aux + 12 * 256;
-#pragma unroll 1
+#pragma unroll
             for (int gI = 0; gI < 4; ++gI) {
               const int col0 = h * 128 + gI * 32;
-              float v[32];
-              tmem_ld32(tmem + lane_base + tl * 256 + col0, v);
+              uint32_t v[32];
+              tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
+              float4 bc[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bc[i] = bnext[i];
+              if (gI < 3) {
+                const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
+              }
+              tmem_ld32_wait(v);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                const float4 b0 = bc[2 * c8], b1 = bc[2 * c8 + 1];
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float x[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  x[e] = v[c8 * 8 + e] + bb[e];
+                  x[e] = __uint_as_float(v[c8 * 8 + e]) + bb[e];
                   if (s < 8) x[e] = fmaxf(x[e], 0.f);                    // mlp.py:33-34 (features is linear: :42)
                 }
                 if (s == 7) {                                            // sigma head on the fp32 h7 (mlp.py:40)
@@ -266,23 +283,37 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
             const float* wrgb = aux + 13 * 256;
             float pr = 0.f, pg = 0.f, pb = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int gI = 0; gI < 2; ++gI) {
               const int col0 = h * 64 + gI * 32;
-              float v[32];
-              tmem_ld32(tmem + lane_base + tl * 256 + col0, v);
+              uint32_t v[32];
+              tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
+              float4 bc[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bc[i] = bnext[i];
+              if (gI < 1) {
+                const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
+              }
+              tmem_ld32_wait(v);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                const float4 b0 = bc[2 * c8], b1 = bc[2 * c8 + 1];
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                // rgb kernel rows col..col+7: 24 consecutive floats, 16-byte aligned (col % 8 == 0)
+                float wv[24];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrgb + col * 3) + i);
+                  wv[4 * i] = w4.x; wv[4 * i + 1] = w4.y; wv[4 * i + 2] = w4.z; wv[4 * i + 3] = w4.w;
+                }
                 float x[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  x[e] = v[c8 * 8 + e] + bb[e];
-                  const float* wr = wrgb + (col + e) * 3;
-                  pr += x[e] * __ldg(wr); pg += x[e] * __ldg(wr + 1); pb += x[e] * __ldg(wr + 2);
+                  x[e] = __uint_as_float(v[c8 * 8 + e]) + bb[e];
+                  pr += x[e] * wv[3 * e]; pg += x[e] * wv[3 * e + 1]; pb += x[e] * wv[3 * e + 2];
                 }
                 if (save) {
                   const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),

@@ -105,10 +105,18 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
           float* db = grads + (b == 0 ? P.b_off[9] : P.b_off[zi]);
           const float dsig = dsig_keep[tl];
+          // the ReLU masks do not depend on the accumulator: fetch all 16 vectors of this thread's 128 columns
+          // from HBM BEFORE waiting for the MMA so that their latency overlaps it (was the top stall: long_sb)
+          uint4 hm[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hm[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (b >= 1 && active) hm[i] = __ldg(reinterpret_cast<const uint4*>(mask + (h * 16 + i) * kChunkA + r * 16));
+          }
           mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
-#pragma unroll 1
+#pragma unroll
           for (int gI = 0; gI < 4; ++gI) {
             const int col0 = h * 128 + gI * 32;
             float v[32];
@@ -127,12 +135,11 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
                 x[4] += dsig * w1.x; x[5] += dsig * w1.y; x[6] += dsig * w1.z; x[7] += dsig * w1.w;
               }
               if (b >= 1) {   // ReLU': pass where the saved forward activation is > 0
-                uint4 hm = make_uint4(0u, 0u, 0u, 0u);
-                if (active) hm = __ldg(reinterpret_cast<const uint4*>(mask + off));
-                x[0] = bf16_lo(hm.x) > 0.f ? x[0] : 0.f; x[1] = bf16_hi(hm.x) > 0.f ? x[1] : 0.f;
-                x[2] = bf16_lo(hm.y) > 0.f ? x[2] : 0.f; x[3] = bf16_hi(hm.y) > 0.f ? x[3] : 0.f;
-                x[4] = bf16_lo(hm.z) > 0.f ? x[4] : 0.f; x[5] = bf16_hi(hm.z) > 0.f ? x[5] : 0.f;
-                x[6] = bf16_lo(hm.w) > 0.f ? x[6] : 0.f; x[7] = bf16_hi(hm.w) > 0.f ? x[7] : 0.f;
+                const uint4 m4 = hm[gI * 4 + c8];
+                x[0] = bf16_lo(m4.x) > 0.f ? x[0] : 0.f; x[1] = bf16_hi(m4.x) > 0.f ? x[1] : 0.f;
+                x[2] = bf16_lo(m4.y) > 0.f ? x[2] : 0.f; x[3] = bf16_hi(m4.y) > 0.f ? x[3] : 0.f;
+                x[4] = bf16_lo(m4.z) > 0.f ? x[4] : 0.f; x[5] = bf16_hi(m4.z) > 0.f ? x[5] : 0.f;
+                x[6] = bf16_lo(m4.w) > 0.f ? x[6] : 0.f; x[7] = bf16_hi(m4.w) > 0.f ? x[7] : 0.f;
               }
               const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                           pack_bf16x2(x[6], x[7]));
