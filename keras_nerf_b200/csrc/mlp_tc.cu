@@ -9,7 +9,8 @@
 //   warp 0      TMA producer: streams the pre-packed bf16 weight blob, 32-wide K stages, 4-slot mbarrier ring
 //   warp 1      MMA issuer:   one thread issues tcgen05.mma (M=128, N=256|128, K=16) and tcgen05.commit
 //   warps 2-9   compute:      PE prologue, TMEM -> register epilogues (bias, ReLU, bf16 pack) that write the
-//                             next layer's A operand straight into shared memory, heads, output
+//                             next layer's A operand straight into shared memory, heads, output.
+//                             Biases ride in the GEMM (constant-1 column, tc_layout.cuh).
 // Each CTA keeps TWO 128-sample tiles in flight (accumulators in TMEM columns [0,256) and [256,512)): while
 // the tensor core runs tile 1's layer, the compute warps drain tile 0's accumulator and build its next A
 // operand, and vice versa, so the MMA pipe only waits when an epilogue is slower than a layer of MMAs.
@@ -35,9 +36,17 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
     while (s + 1 < FwdProg::kSteps && byte >= FwdProg::blob_off(s + 1)) ++s;
     const int local = byte - FwdProg::blob_off(s);
     const int N = FwdProg::N(s), sb = FwdProg::stage_bytes(s);
+    const int L = FwdProg::layer(s);
+    const int nks = FwdProg::nk_h(s) + FwdProg::nk_x(s);
+    if (local >= nks * sb) {   // bias chunk [2 chunks][N][8]: k = 15 <- bias[n], everything else 0
+      const int rb = local - nks * sb;
+      const int cb = rb / (N * 16), nb = (rb - cb * N * 16) / 16;
+      const uint32_t hi = (cb == 1) ? (pack_bf16x2(0.f, params[P.b_off[L] + nb])) : 0u;
+      *reinterpret_cast<uint4*>(packed + byte) = make_uint4(0u, 0u, 0u, hi);
+      continue;
+    }
     const int ks = local / sb, r = local - ks * sb;
     const int c = r / (N * 16), n = (r - c * N * 16) / 16;
-    const int L = FwdProg::layer(s);
     const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : (L == 10) ? 283 : 256;
     const float* W = params + P.w_off[L];
     int row0;
@@ -101,7 +110,7 @@ __device__ __forceinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, co
 #pragma unroll
     for (int c = 0; c < 3; ++c) store_elem(xs, r, c, p[c]);
   } else {
-    store_elem(xs, r, 63, 0.f);
+    store_elem(xs, r, 63, 1.f);   // constant-1 column: carries the folded bias (tc_layout.cuh)
   }
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
@@ -130,7 +139,8 @@ __device__ __forceinline__ void pe_dir(uint8_t* xs, int r, int h, bool valid, co
     for (int c = 0; c < 3; ++c) store_elem(xs, r, c, v[c]);
   } else {
 #pragma unroll
-    for (int c = 27; c < 32; ++c) store_elem(xs, r, c, 0.f);
+    for (int c = 27; c < 31; ++c) store_elem(xs, r, c, 0.f);
+    store_elem(xs, r, 31, 1.f);   // constant-1 column for the folded bias of steps 6..9
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -196,7 +206,6 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int s = 0; s < FwdProg::kSteps; ++s) {
-        const float* bias = aux + FwdProg::layer(s) * 256;
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = pair * 2 + tl;
@@ -204,21 +213,13 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           const bool valid = g < M;
           const bool save = TRAIN && tile < n_tiles;
           uint8_t* rec_t = rec + tile * kRecBytes;
-          // software pipeline against load latency (the epilogue is the critical path): the bias vectors of a
-          // 32-column group are fetched before the accumulator is waited for / while the previous group's
-          // TMEM load is in flight
-          float4 bnext[8];
-          {
-            const float4* bp = reinterpret_cast<const float4*>(bias + (s < 9 ? h * 128 : h * 64));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
-          }
           mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
 
           if (s < 9) {
-            // hidden layers (bias + ReLU) and `features` (bias, linear): 128 of the 256 columns per thread
+            // hidden layers (ReLU) and `features` (linear): 128 of the 256 columns per thread.  The bias is
+            // already in the accumulator (folded into the GEMM), ReLU is fused into the bf16 conversion.
             uint8_t* rec_out = rec_t + (s < 8 ? kRecH0 + s * kHSBytes : kRecF);
             float sigdot = 0.f;
             const float* wsig = aux + 12 * 256;
@@ -227,34 +228,30 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               const int col0 = h * 128 + gI * 32;
               uint32_t v[32];
               tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
-              float4 bc[8];
+              float4 ws[8];
+              if (s == 7) {   // sigma kernel for these 32 columns, fetched while the TMEM load is in flight
 #pragma unroll
-              for (int i = 0; i < 8; ++i) bc[i] = bnext[i];
-              if (gI < 3) {
-                const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 32);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
+                for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
               }
               tmem_ld32_wait(v);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
-                const float4 b0 = bc[2 * c8], b1 = bc[2 * c8 + 1];
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float x[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  x[e] = __uint_as_float(v[c8 * 8 + e]) + bb[e];
-                  if (s < 8) x[e] = fmaxf(x[e], 0.f);                    // mlp.py:33-34 (features is linear: :42)
+                const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
+                uint4 pk;
+                if (s < 8) {                                             // mlp.py:33-34
+                  pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
+                                  pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
+                } else {                                                 // features is linear (mlp.py:42)
+                  pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                  pack_bf16x2(x[6], x[7]));
                 }
                 if (s == 7) {                                            // sigma head on the fp32 h7 (mlp.py:40)
-                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + col));
-                  const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + col + 4));
-                  sigdot += x[0] * w0.x + x[1] * w0.y + x[2] * w0.z + x[3] * w0.w + x[4] * w1.x + x[5] * w1.y +
-                            x[6] * w1.z + x[7] * w1.w;
+                  const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
+                  sigdot += fmaxf(x[0], 0.f) * w0.x + fmaxf(x[1], 0.f) * w0.y + fmaxf(x[2], 0.f) * w0.z +
+                            fmaxf(x[3], 0.f) * w0.w + fmaxf(x[4], 0.f) * w1.x + fmaxf(x[5], 0.f) * w1.y +
+                            fmaxf(x[6], 0.f) * w1.z + fmaxf(x[7], 0.f) * w1.w;
                 }
-                const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                            pack_bf16x2(x[6], x[7]));
                 const int off = (col >> 3) * kChunkA + r * 16;
                 *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;        // next layer's A operand, in place
                 if (save) *reinterpret_cast<uint4*>(rec_out + off) = pk;
@@ -288,32 +285,20 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               const int col0 = h * 64 + gI * 32;
               uint32_t v[32];
               tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
-              float4 bc[8];
+              // rgb kernel rows col0..col0+31: 96 consecutive floats, 16-byte aligned; fetched under the TMEM load
+              float4 wq[24];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) bc[i] = bnext[i];
-              if (gI < 1) {
-                const float4* bp = reinterpret_cast<const float4*>(bias + col0 + 32);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bnext[i] = __ldg(bp + i);
-              }
+              for (int i = 0; i < 24; ++i) wq[i] = __ldg(reinterpret_cast<const float4*>(wrgb + col0 * 3) + i);
               tmem_ld32_wait(v);
+              const float* wv = reinterpret_cast<const float*>(wq);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
-                const float4 b0 = bc[2 * c8], b1 = bc[2 * c8 + 1];
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                // rgb kernel rows col..col+7: 24 consecutive floats, 16-byte aligned (col % 8 == 0)
-                float wv[24];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrgb + col * 3) + i);
-                  wv[4 * i] = w4.x; wv[4 * i + 1] = w4.y; wv[4 * i + 2] = w4.z; wv[4 * i + 3] = w4.w;
-                }
-                float x[8];
+                const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);   // bias folded, linear (mlp.py:43-46)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  x[e] = __uint_as_float(v[c8 * 8 + e]) + bb[e];
-                  pr += x[e] * wv[3 * e]; pg += x[e] * wv[3 * e + 1]; pb += x[e] * wv[3 * e + 2];
+                  const int j = (c8 * 8 + e) * 3;
+                  pr += x[e] * wv[j]; pg += x[e] * wv[j + 1]; pb += x[e] * wv[j + 2];
                 }
                 if (save) {
                   const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),

@@ -134,15 +134,13 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
                 x[0] += dsig * w0.x; x[1] += dsig * w0.y; x[2] += dsig * w0.z; x[3] += dsig * w0.w;
                 x[4] += dsig * w1.x; x[5] += dsig * w1.y; x[6] += dsig * w1.z; x[7] += dsig * w1.w;
               }
-              if (b >= 1) {   // ReLU': pass where the saved forward activation is > 0
+              uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                                    pack_bf16x2(x[6], x[7]));
+              if (b >= 1) {   // ReLU': keep where the saved forward activation is > 0 (HSET2.BF16 mask + AND)
                 const uint4 m4 = hm[gI * 4 + c8];
-                x[0] = bf16_lo(m4.x) > 0.f ? x[0] : 0.f; x[1] = bf16_hi(m4.x) > 0.f ? x[1] : 0.f;
-                x[2] = bf16_lo(m4.y) > 0.f ? x[2] : 0.f; x[3] = bf16_hi(m4.y) > 0.f ? x[3] : 0.f;
-                x[4] = bf16_lo(m4.z) > 0.f ? x[4] : 0.f; x[5] = bf16_hi(m4.z) > 0.f ? x[5] : 0.f;
-                x[6] = bf16_lo(m4.w) > 0.f ? x[6] : 0.f; x[7] = bf16_hi(m4.w) > 0.f ? x[7] : 0.f;
+                pk.x &= bf16x2_gt0_mask(m4.x); pk.y &= bf16x2_gt0_mask(m4.y);
+                pk.z &= bf16x2_gt0_mask(m4.z); pk.w &= bf16x2_gt0_mask(m4.w);
               }
-              const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                          pack_bf16x2(x[6], x[7]));
               *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
               if (active) *reinterpret_cast<uint4*>(out + off) = pk;
             }

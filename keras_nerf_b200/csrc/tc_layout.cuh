@@ -28,9 +28,18 @@ struct FwdProg {
   __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 9 ? 1 : 0); }
   __host__ __device__ static constexpr int N(int s) { return s == 9 ? 128 : 256; }
   __host__ __device__ static constexpr int stage_bytes(int s) { return N(s) * kKStage * 2; }
+  // Bias folded into the GEMM: every step ends with ONE extra K=16 MMA whose A operand is two chunks of the
+  // encoding buffer that contain a constant-1 column (PE(xyz) pad column 63 for steps 0..5, PE(dir) pad column
+  // 31 afterwards) and whose B operand [2 chunks][N][8] is zero except k = 15 <- bias[n].  The real weight rows
+  // of those pad columns are zero, so the 1.0 never leaks into the ordinary stages.  Costs 1/16 more MMA time,
+  // removes every bias load and add from the epilogue (which is the critical path).
+  static constexpr bool kHasBias = true;
+  __host__ __device__ static constexpr int bias_bytes(int s) { return N(s) * 32; }
+  __host__ __device__ static constexpr int bias_a_chunk(int s) { return s <= 5 ? 6 : 2; }
+  __host__ __device__ static constexpr int step_bytes(int s) { return (nk_h(s) + nk_x(s)) * stage_bytes(s) + bias_bytes(s); }
   __host__ __device__ static constexpr int blob_off(int s) {
     int off = 0;
-    for (int i = 0; i < s; ++i) off += (nk_h(i) + nk_x(i)) * stage_bytes(i);
+    for (int i = 0; i < s; ++i) off += step_bytes(i);
     return off;
   }
 };
@@ -47,6 +56,9 @@ struct BwdProg {
   __host__ __device__ static constexpr int nk_x(int) { return 0; }
   __host__ __device__ static constexpr int N(int) { return 256; }
   __host__ __device__ static constexpr int stage_bytes(int) { return kStageBytes; }
+  static constexpr bool kHasBias = false;
+  __host__ __device__ static constexpr int bias_bytes(int) { return 0; }
+  __host__ __device__ static constexpr int bias_a_chunk(int) { return 0; }
   __host__ __device__ static constexpr int blob_off(int b) { return (b == 0 ? 0 : 4 + (b - 1) * 8) * kStageBytes; }
   __host__ __device__ static constexpr int ld(int b) { return b == 0 ? 128 : 256; }       // fan_out of that kernel
 };

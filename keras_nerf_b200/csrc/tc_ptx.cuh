@@ -165,6 +165,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// max(.,0) fused into the conversion (F2FP.RELU.BF16.F32.PACK_AB): low half = lo, high half = hi
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// per-half 0xffff where the bf16 value is > 0 (HSET2.BF16.GT): AND-mask for ReLU'
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t p) {
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(p), "r"(0u));
+  return m;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 

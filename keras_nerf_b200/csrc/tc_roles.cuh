@@ -45,6 +45,13 @@ __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __re
           mbar_arrive_expect_tx(&sm.full[slot], sb);
           tma_load_1d(sm.stage[slot], src + (size_t)ks * sb, sb, &sm.full[slot]);
         }
+        if (Prog::kHasBias) {   // the bias "stage": [2 chunks][N][8]
+          const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1, bb = Prog::bias_bytes(s);
+          mbar_wait(&sm.empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&sm.full[slot], bb);
+          tma_load_1d(sm.stage[slot], src + (size_t)nk * sb, bb, &sm.full[slot]);
+          ++it;
+        }
       }
     }
   }
@@ -79,6 +86,16 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
             umma_bf16(d_tmem, da, db, idesc, (ks > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(&sm.empty[slot]);
+        }
+        if (Prog::kHasBias) {   // + 1 * bias: A = the two encoding chunks holding the constant-1 column
+          const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1;
+          mbar_wait(&sm.full[slot], ph);
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc(smem_u32(sm.xs[tl]) + Prog::bias_a_chunk(s) * kChunkA, kChunkA, 128);
+          const uint64_t db = umma_smem_desc(smem_u32(sm.stage[slot]), chunk_b, 128);
+          umma_bf16(d_tmem, da, db, idesc, 1u);
+          umma_commit(&sm.empty[slot]);
+          ++it;
         }
         umma_commit(&sm.acc_ready[tl]);
       }
