@@ -97,7 +97,7 @@ __device__ __forceinline__ void store_elem(uint8_t* base, int r, int col, float 
 }
 
 // PE_10(o + d t) -> 63 columns (+ zero pad column 63): h=0 writes identity + frequencies 0..4, h=1 5..9
-__device__ __forceinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ o,
+__device__ __noinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ o,
                                        const float* __restrict__ d, const float* __restrict__ t, int64_t g, int S) {
   float p[3] = {0.f, 0.f, 0.f};
   if (valid) {
@@ -112,7 +112,7 @@ __device__ __forceinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, co
   } else {
     store_elem(xs, r, 63, 1.f);   // constant-1 column: carries the folded bias (tc_layout.cuh)
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 5; ++i) {
     const int f = h * 5 + i;
 #pragma unroll
@@ -126,7 +126,7 @@ __device__ __forceinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, co
 }
 
 // PE_4(d) -> 27 columns (+ zero pad 27..31) into chunks 0..3 of the xs buffer; h=0: identity + f 0,1; h=1: f 2,3
-__device__ __forceinline__ void pe_dir(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ d, int64_t g,
+__device__ __noinline__ void pe_dir(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ d, int64_t g,
                                        int S) {
   float v[3] = {0.f, 0.f, 0.f};
   if (valid) {
@@ -142,7 +142,7 @@ __device__ __forceinline__ void pe_dir(uint8_t* xs, int r, int h, bool valid, co
     for (int c = 27; c < 31; ++c) store_elem(xs, r, c, 0.f);
     store_elem(xs, r, 31, 1.f);   // constant-1 column for the folded bias of steps 6..9
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 2; ++i) {
     const int f = h * 2 + i;
 #pragma unroll
@@ -186,7 +186,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
-    float sig_keep[2] = {0.f, 0.f};
+    float sig_keep0 = 0.f, sig_keep1 = 0.f;   // sigma of this thread's row, per tile slot
 
     auto prologue = [&](int64_t pair, int tl) {
       const int64_t tile = pair * 2 + tl;
@@ -201,12 +201,12 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     };
 
     if ((int64_t)blockIdx.x < n_pairs) {
-      prologue(blockIdx.x, 0);
-      prologue(blockIdx.x, 1);
+#pragma unroll 1
+      for (int tl = 0; tl < 2; ++tl) prologue(blockIdx.x, tl);
     }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int s = 0; s < FwdProg::kSteps; ++s) {
-#pragma unroll
+#pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = pair * 2 + tl;
           const int64_t g = tile * kTileM + r;
@@ -223,7 +223,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             uint8_t* rec_out = rec_t + (s < 8 ? kRecH0 + s * kHSBytes : kRecF);
             float sigdot = 0.f;
             const float* wsig = aux + 12 * 256;
-#pragma unroll
+#pragma unroll 1
             for (int gI = 0; gI < 4; ++gI) {
               const int col0 = h * 128 + gI * 32;
               uint32_t v[32];
@@ -260,7 +260,10 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             if (s == 7) {
               if (h == 1) sm.part[r][0] = sigdot;
               named_bar_sync(1, kComputeThreads);
-              if (h == 0) sig_keep[tl] = fmaxf(sigdot + sm.part[r][0] + __ldg(aux + 8 * 256), 0.f);
+              if (h == 0) {
+                const float sg = fmaxf(sigdot + sm.part[r][0] + __ldg(aux + 8 * 256), 0.f);
+                if (tl == 0) sig_keep0 = sg; else sig_keep1 = sg;
+              }
               named_bar_sync(1, kComputeThreads);
             }
             if (s == 5) {
@@ -280,7 +283,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
             const float* wrgb = aux + 13 * 256;
             float pr = 0.f, pg = 0.f, pb = 0.f;
-#pragma unroll
+#pragma unroll 1
             for (int gI = 0; gI < 2; ++gI) {
               const int col0 = h * 64 + gI * 32;
               uint32_t v[32];
@@ -314,7 +317,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               const float zr = pr + sm.part[r][0] + __ldg(brgb), zg = pg + sm.part[r][1] + __ldg(brgb + 1),
                           zb = pb + sm.part[r][2] + __ldg(brgb + 2);
               rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)),
-                                        sig_keep[tl]);
+                                        tl == 0 ? sig_keep0 : sig_keep1);
             }
             named_bar_sync(1, kComputeThreads);
             tc_fence_before();

@@ -46,7 +46,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     const float* wsig = aux + 12 * 256;
     const float* wrgb = aux + 13 * 256;
     uint32_t acc_par[2] = {0, 0};
-    float dsig_keep[2] = {0.f, 0.f};
+    float dsig_keep0 = 0.f, dsig_keep1 = 0.f;
 
     // tile start: dG = d(rgb_pre) Wc^T (K = 3, CUDA cores) becomes the first A operand
     auto prologue = [&](int64_t pair, int tl) {
@@ -55,7 +55,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       const bool active = tile < n_tiles;
       float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < M) dp = d_pre[g];
-      dsig_keep[tl] = dp.w;
+      if (tl == 0) dsig_keep0 = dp.w; else dsig_keep1 = dp.w;
       uint8_t* dz_t = dz + tile * kDzBytes;
       if (active) {
         const uint4 pk = (h == 0) ? make_uint4(pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u)
@@ -91,20 +91,20 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     };
 
     if ((int64_t)blockIdx.x < n_pairs) {
-      prologue(blockIdx.x, 0);
-      prologue(blockIdx.x, 1);
+#pragma unroll 1
+      for (int tl = 0; tl < 2; ++tl) prologue(blockIdx.x, tl);
     }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int b = 0; b < BwdProg::kSteps; ++b) {
         const int zi = 8 - b;                                  // index of the dZ this step produces (b >= 1)
-#pragma unroll
+#pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = pair * 2 + tl;
           const bool active = tile < n_tiles;
           uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
           const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
           float* db = grads + (b == 0 ? P.b_off[9] : P.b_off[zi]);
-          const float dsig = dsig_keep[tl];
+          const float dsig = tl == 0 ? dsig_keep0 : dsig_keep1;
           // the ReLU masks do not depend on the accumulator: fetch all 16 vectors of this thread's 128 columns
           // from HBM BEFORE waiting for the MMA so that their latency overlaps it (was the top stall: long_sb)
           uint4 hm[16];

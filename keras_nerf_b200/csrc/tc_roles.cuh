@@ -105,7 +105,7 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
 
 // column sums of a [128 x ncols] bf16 operand sitting in shared memory (chunk-major) -> atomically added to
 // dst[0..ncols) (bias gradients).  All 256 compute threads; caller has synchronised them after the writes.
-__device__ __forceinline__ void colsum_to_global(const uint8_t* hs, int ncols, float* __restrict__ dst, int ctid) {
+static __device__ __noinline__ void colsum_to_global(const uint8_t* hs, int ncols, float* __restrict__ dst, int ctid) {
   const int c = ctid >> 3, sub = ctid & 7;
   if (c * 8 < ncols) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
