@@ -40,7 +40,6 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
   } else {
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int ctid = tid - 64;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     const float* wsig = aux + 12 * 256;
@@ -86,8 +85,6 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       }
       fence_async_smem();
       mbar_arrive(&sm.a_ready[tl]);
-      named_bar_sync(1, kComputeThreads);
-      colsum_to_global(sm.hs[tl], 128, grads + P.b_off[10], ctid);     // db of rgb_features
     };
 
     if ((int64_t)blockIdx.x < n_pairs) {
@@ -103,7 +100,6 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           const bool active = tile < n_tiles;
           uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
           const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
-          float* db = grads + (b == 0 ? P.b_off[9] : P.b_off[zi]);
           const float dsig = tl == 0 ? dsig_keep0 : dsig_keep1;
           // the ReLU masks do not depend on the accumulator: fetch all 16 vectors of this thread's 128 columns
           // from HBM BEFORE waiting for the MMA so that their latency overlaps it (was the top stall: long_sb)
@@ -141,21 +137,19 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
                 pk.x &= bf16x2_gt0_mask(m4.x); pk.y &= bf16x2_gt0_mask(m4.y);
                 pk.z &= bf16x2_gt0_mask(m4.z); pk.w &= bf16x2_gt0_mask(m4.w);
               }
-              *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
+              // dZ0 (last step) feeds no further GEMM: it must NOT touch hs[tl], which the other half-row thread
+              // of this row may already be rebuilding for the next tile (prologue below)
+              if (b + 1 < BwdProg::kSteps) *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
               if (active) *reinterpret_cast<uint4*>(out + off) = pk;
             }
           }
           tc_fence_before();
           fence_async_smem();
           if (b + 1 < BwdProg::kSteps) mbar_arrive(&sm.a_ready[tl]);
-          named_bar_sync(1, kComputeThreads);
-          colsum_to_global(sm.hs[tl], 256, db, ctid);
           if (b + 1 == BwdProg::kSteps) {
+            // (bias gradients = column sums of the dZ tiles are taken by tc_wgrad_kernel, which has them in smem)
             const int64_t next = pair + gridDim.x;
-            if (next < n_pairs) {
-              named_bar_sync(1, kComputeThreads);   // everyone is done reading hs[tl] before it is rebuilt
-              prologue(next, tl);
-            }
+            if (next < n_pairs) prologue(next, tl);
           }
         }
       }
@@ -172,7 +166,8 @@ constexpr int kWSlots = 6;
 constexpr int kWThreads = 192;         // warp 0 producer, warp 1 MMA, warps 2-5 flush
 constexpr int kNumTasks = 13;
 
-struct WUnit { int src, off, bytes; };                       // src 0 = forward record, 1 = dz record
+struct WUnit { int src, off, bytes, bias_layer, bias_col0; };   // src 0 = forward record, 1 = dz record;
+                                                                // bias_layer >= 0: column sums of this dZ unit are db
 struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b; };
 struct WTask { int n_units; WUnit u[4]; int n_groups; WGroup g[4]; int cost; };
 // mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
@@ -185,8 +180,8 @@ static WTaskTable build_task_table() {
   auto big = [&](int layer, int a_off, int b_off, int row_base) {   // A: two 128-feature halves, B: two 128-output halves
     WTask& t = T.t[n++];
     t.n_units = 4;
-    t.u[0] = {0, a_off, kWUnitBytes}; t.u[1] = {1, b_off, kWUnitBytes};
-    t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes}; t.u[3] = {0, a_off + kWUnitBytes, kWUnitBytes};
+    t.u[0] = {0, a_off, kWUnitBytes, -1, 0}; t.u[1] = {1, b_off, kWUnitBytes, layer, 0};
+    t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes, layer, 128}; t.u[3] = {0, a_off + kWUnitBytes, kWUnitBytes, -1, 0};
     t.n_groups = 4;
     t.g[0] = {0, 1, 0, 128, layer, row_base, 128, 0, 0, 0, 0};
     t.g[1] = {0, 2, 128, 128, layer, row_base, 128, 128, 0, 1, 0};
@@ -197,7 +192,9 @@ static WTaskTable build_task_table() {
   auto xpart = [&](int layer, int b_off, int row_base) {           // A: PE(xyz) (63 valid rows), B: two halves
     WTask& t = T.t[n++];
     t.n_units = 3;
-    t.u[0] = {0, kRecXS, kWUnitBytes}; t.u[1] = {1, b_off, kWUnitBytes}; t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes};
+    const int bl = (layer == 0) ? 0 : -1;   // layer 5's dZ column sums are taken by its h-part task
+    t.u[0] = {0, kRecXS, kWUnitBytes, -1, 0}; t.u[1] = {1, b_off, kWUnitBytes, bl, 0};
+    t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes, bl, 128};
     t.n_groups = 2;
     t.g[0] = {0, 1, 0, 128, layer, row_base, 63, 0, 0, 0, 1};
     t.g[1] = {0, 2, 128, 128, layer, row_base, 63, 128, 0, 1, 1};
@@ -210,8 +207,8 @@ static WTaskTable build_task_table() {
   {  // sigma (A = h7 halves) and rgb (A = rgb_features) against the packed d_pre operand (N = 16)
     WTask& t = T.t[n++];
     t.n_units = 4;
-    t.u[0] = {1, kDzP, 4096}; t.u[1] = {0, kRecH0 + 7 * kHSBytes, kWUnitBytes};
-    t.u[2] = {0, kRecH0 + 7 * kHSBytes + kWUnitBytes, kWUnitBytes}; t.u[3] = {0, kRecG, kWUnitBytes};
+    t.u[0] = {1, kDzP, 4096, -1, 0}; t.u[1] = {0, kRecH0 + 7 * kHSBytes, kWUnitBytes, -1, 0};
+    t.u[2] = {0, kRecH0 + 7 * kHSBytes + kWUnitBytes, kWUnitBytes, -1, 0}; t.u[3] = {0, kRecG, kWUnitBytes, -1, 0};
     t.n_groups = 3;
     t.g[0] = {1, 0, 0, 16, 8, 0, 128, 0, 1, 1, 0};
     t.g[1] = {2, 0, 32, 16, 8, 128, 128, 0, 1, 1, 0};
@@ -221,8 +218,8 @@ static WTaskTable build_task_table() {
   {  // rgb_features: A = features halves + PE(dir) (27 valid rows), B = dG (N = 128)
     WTask& t = T.t[n++];
     t.n_units = 4;
-    t.u[0] = {1, kDzG, kWUnitBytes}; t.u[1] = {0, kRecF, kWUnitBytes}; t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes};
-    t.u[3] = {0, kRecDS, kWUnitBytes};
+    t.u[0] = {1, kDzG, kWUnitBytes, 10, 0}; t.u[1] = {0, kRecF, kWUnitBytes, -1, 0};
+    t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes, -1, 0}; t.u[3] = {0, kRecDS, kWUnitBytes, -1, 0};
     t.n_groups = 3;
     t.g[0] = {1, 0, 0, 128, 10, 0, 128, 0, 0, 1, 0};
     t.g[1] = {2, 0, 128, 128, 10, 128, 128, 0, 0, 1, 0};
@@ -272,7 +269,8 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
   WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < kWSlots; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    // a slot is free again when the MMAs that read it have completed AND the flush warps are done with it
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 2); }
     mbar_init(&sm.acc_done, 1);
     mbar_init(&sm.acc_free, 128);
     fence_mbar_init();
@@ -341,11 +339,59 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
     // flush warps: TMEM lane quadrant = warp & 3
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t done_par = 0;
+    const int ftid = tid - 64, fc = ftid >> 3, fsub = ftid & 7;
+    uint32_t done_par = 0, uit = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const WItem w = decode_item(T, item, slabs, n_tiles);
       const WTask& t = T.t[w.task];
       if (w.tile_lo >= w.tile_hi) continue;
+      // While the tensor core works through the item, these warps take the bias gradients: column sums (over
+      // samples) of every dZ unit passing through shared memory.  Thread (fc, fsub) owns 8 columns of chunk fc
+      // and every 8th sample; partial sums stay in registers for the whole item.
+      float bacc[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bacc[u][e] = 0.f;
+      for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile) {
+        int nb = 0;
+        for (int k = 0; k < t.n_units; ++k, ++uit) {
+          const uint32_t slot = uit % kWSlots;
+          mbar_wait(&sm.full[slot], (uit / kWSlots) & 1);
+          if (t.u[k].bias_layer >= 0) {
+            const uint8_t* base = sm.slot[slot] + fc * kChunkA + fsub * 16;
+            float* a = bacc[nb & 1];
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const uint4 v = *reinterpret_cast<const uint4*>(base + i * 128);
+              a[0] += bf16_lo(v.x); a[1] += bf16_hi(v.x); a[2] += bf16_lo(v.y); a[3] += bf16_hi(v.y);
+              a[4] += bf16_lo(v.z); a[5] += bf16_hi(v.z); a[6] += bf16_lo(v.w); a[7] += bf16_hi(v.w);
+            }
+            ++nb;
+          }
+          named_bar_sync(2, 128);               // all 128 readers are done with the slot
+          if (ftid == 0) mbar_arrive(&sm.empty[slot]);
+        }
+      }
+      {
+        int nb = 0;
+        for (int k = 0; k < t.n_units; ++k) {
+          if (t.u[k].bias_layer < 0) continue;
+          float* a = bacc[nb & 1];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 1);
+            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 2);
+            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 4);
+          }
+          if (fsub == 0) {
+            float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + fc * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e]);
+          }
+          ++nb;
+        }
+      }
       mbar_wait(&sm.acc_done, done_par);
       done_par ^= 1;
       tc_fence_after();
