@@ -253,6 +253,7 @@ def main():
     if rank != 0:
         if strategy is not None:
             strategy.barrier()
+            torch.distributed.destroy_process_group()
         return
     peaks = load_peaks()
     total_rays = RAYS_PER_GPU * world * args.steps
@@ -282,6 +283,7 @@ def main():
     print(json.dumps(line), flush=True)
     if strategy is not None:
         strategy.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,18 +1,28 @@
-"""Roofline numbers for bench.py: the dominant kernel timed alone with CUDA events on the launching stream
-(burst peaks apply), and the secondary BASELINE metric (800x800 render ms/frame)."""
+"""Roofline numbers for bench.py: each MLP kernel of the training step timed alone with CUDA events on the
+launching stream (burst peaks apply), and the secondary BASELINE metric (800x800 render ms/frame)."""
 import ctypes as C
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FLOP_FWD_PER_SAMPLE = 1_186_816
-FLOP_TRAIN_PER_SAMPLE = 3_489_024
+# algorithmic work per sample (unpadded shapes)
+FLOP_FWD_PER_SAMPLE = 1_186_816            # 593,408 MAC
+FLOP_TRAIN_PER_SAMPLE = 3_489_024          # fwd + dgrad + wgrad
+FLOP_WGRAD_PER_SAMPLE = 1_186_816          # every weight once more
+FLOP_DGRAD_PER_SAMPLE = FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE - FLOP_WGRAD_PER_SAMPLE
+# bf16 mode, algorithmic HBM bytes per sample (records of 640 KB + 612 KB per 128 samples)
+BYTES_FWD_SAVE = 640 * 1024 / 128                       # forward writes the activation record once
+BYTES_DGRAD = 8 * 512 + 612 * 1024 / 128                # reads the 8 ReLU-mask tiles, writes the dZ record
+BYTES_WGRAD = 1444 * 1024 / 128                         # operand units of the 12 weight-gradient tasks
+# measured DRAM traffic per sample from `ncu --set full` (profiles/r01_bf16_ncu_full.md, 393,216-sample launches)
+NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.035415 + 1.963989) * 1e9 / 393216,
+                          "tc_mlp_dgrad_kernel": (1.629502 + 1.882920) * 1e9 / 393216,
+                          "tc_wgrad_kernel": (4.524511 + 0.005662) * 1e9 / 393216}
 
 
 def _time_ms(fn, iters=5, warmup=2):
@@ -29,8 +39,8 @@ def _time_ms(fn, iters=5, warmup=2):
 
 
 def dominant_kernel_roofline(model, precision, peaks):
-    """MLP stage of the fine network (the > 95 % FLOP stage): forward and backward timed separately on the
-    training shapes of the bench (R = ray_chunks rays x 192 samples)."""
+    """The MLP kernels of the fine network (> 95 % of the step) on the bench's training shapes
+    (R = ray_chunks rays x 192 samples), each timed alone; `roofline` names the one with the largest time."""
     from keras_nerf_b200 import _lib
     dev = model.device
     R, S = model.ray_chunks, model.n_coarse + model.n_fine
@@ -56,27 +66,56 @@ def dominant_kernel_roofline(model, precision, peaks):
         _lib.call("knerf_mlp_backward", C.byref(model.cfg), _lib.ptr(model.fine.params), packed, _lib.ptr(dpre), R, S,
                   prec, _lib.ptr(grads), ws, wsn, _lib.stream())
 
+    bf16_peak, hbm_peak = peaks["bf16_tflops"], peaks["hbm_gbs"]
+    src = f"{peaks['source']} (MEASURED_PEAKS.json: cuBLAS bf16 burst, copy bandwidth)"
+    kernels = {}
+
+    def add(name, ms, flop_ps, bytes_ps, launches):
+        tf = flop_ps * rows / (ms * 1e-3) / 1e12
+        k = {"ms": ms, "launches": launches, "tflops": tf, "tensor_frac": tf / bf16_peak}
+        if bytes_ps:
+            gb = bytes_ps * rows / (ms * 1e-3) / 1e9
+            k.update({"hbm_GBps": gb, "hbm_frac": gb / hbm_peak, "algorithmic_bytes_per_sample": bytes_ps})
+        if name in NCU_TRAFFIC_PER_SAMPLE:
+            k["ncu_dram_bytes_per_sample"] = NCU_TRAFFIC_PER_SAMPLE[name]
+        k["algorithmic_flop_per_sample"] = flop_ps
+        kernels[name] = k
+
     l0 = lib.knerf_launch_count()
     fwd()
-    l1 = lib.knerf_launch_count()
-    bwd()
-    l2 = lib.knerf_launch_count()
+    n_f = int(lib.knerf_launch_count() - l0)
     ms_f = _time_ms(fwd)
-    ms_b = _time_ms(bwd)
-    tf_f = FLOP_FWD_PER_SAMPLE * rows / (ms_f * 1e-3) / 1e12
-    tf_b = (FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE) * rows / (ms_b * 1e-3) / 1e12
-    peak = peaks["bf16_tflops"]
-    dominant = "mlp_backward" if ms_b > ms_f else "mlp_forward"
-    ach = tf_b if ms_b > ms_f else tf_f
-    kernel = ("sgemm_kernel/wgrad_kernel (fp32 SIMT FFMA; measured against the bf16 tensor peak)"
-              if precision == "fp32" else "tc_mlp (tcgen05 bf16)")
-    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "peak_source": f"{peaks['source']} burst bf16 (MEASURED_PEAKS.json)", "kernel": kernel, "stage": dominant,
-            "algorithmic_flop_per_sample": {"forward": FLOP_FWD_PER_SAMPLE,
-                                            "backward": FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE},
-            "samples_per_launch": rows,
-            "forward": {"ms": ms_f, "tflops": tf_f, "frac": tf_f / peak, "launches": int(l1 - l0)},
-            "backward": {"ms": ms_b, "tflops": tf_b, "frac": tf_b / peak, "launches": int(l2 - l1)}}
+    if precision == "bf16":
+        add("tc_mlp_fwd_kernel<train>", ms_f, FLOP_FWD_PER_SAMPLE, BYTES_FWD_SAVE, n_f)
+        for name, mask, flop, byt in (("tc_mlp_dgrad_kernel", 1, FLOP_DGRAD_PER_SAMPLE, BYTES_DGRAD),
+                                      ("tc_wgrad_kernel", 2, FLOP_WGRAD_PER_SAMPLE, BYTES_WGRAD)):
+            lib.knerf_debug_backward_parts(mask)
+            try:
+                add(name, _time_ms(bwd), flop, byt, 1)
+            finally:
+                lib.knerf_debug_backward_parts(3)
+    else:
+        add("fp32 forward (13 launches: encode + 12 sgemm_kernel)", ms_f, FLOP_FWD_PER_SAMPLE, None, n_f)
+        l0 = lib.knerf_launch_count()
+        bwd()
+        n_b = int(lib.knerf_launch_count() - l0)
+        add("fp32 backward (sgemm_kernel<T> + wgrad_kernel + colsum_kernel)", _time_ms(bwd),
+            FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE, None, n_b)
+
+    name = max(kernels, key=lambda k: kernels[k]["ms"])
+    k = kernels[name]
+    hbm_bound = precision == "bf16" and k.get("hbm_frac", 0) > k["tensor_frac"]
+    roof = {"kernel": name, "samples_per_launch": rows, "peak_source": src, "kernels": kernels}
+    if hbm_bound:
+        roof.update({"bound": "hbm", "achieved": k["hbm_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": k["hbm_frac"],
+                     "traffic": k.get("ncu_dram_bytes_per_sample", 0) * rows or None})
+    else:
+        roof.update({"bound": "tensor", "achieved": k["tflops"], "peak": bf16_peak, "unit": "TFLOP/s",
+                     "frac": k["tensor_frac"],
+                     "traffic": k.get("ncu_dram_bytes_per_sample", 0) * rows or None})
+    if precision != "bf16":
+        roof["note"] = "fp32 SIMT FFMA parity mode measured against the bf16 tensor peak"
+    return roof
 
 
 def render_ms_per_frame(precision, dev, wh=800, frames=2):
@@ -98,6 +137,6 @@ def render_ms_per_frame(precision, dev, wh=800, frames=2):
 
     ms = _time_ms(one, iters=frames, warmup=1)
     samples = wh * wh * (model.n_coarse + model.n_coarse + model.n_fine)
-    return {"metric": "render_ms_per_frame_800x800", "value": ms, "unit": "ms", "n_gpus": 1,
-            "tflops": FLOP_FWD_PER_SAMPLE * samples / (ms * 1e-3) / 1e12, "ray_chunks": 32000,
-            "precision_mode": precision}
+    tf = FLOP_FWD_PER_SAMPLE * samples / (ms * 1e-3) / 1e12
+    return {"metric": "render_ms_per_frame_800x800", "value": ms, "unit": "ms", "n_gpus": 1, "tflops": tf,
+            "ray_chunks": 32000, "precision_mode": precision}

@@ -192,6 +192,10 @@ int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* strea
 /* Diagnostic: one tcgen05 tile, D[128,N] (fp32, row-major) = A[128,K] * B[N,K]^T from bf16 operand blobs in
  * the library's chunk-major layout ([K/8][rows][8] for mode 0 = K-major; [rows/8][K][8] for mode 1 =
  * MN-major, the weight-gradient form).  Pins the UMMA descriptor encoding in tests/test_gpu_tc.py.        */
+/* Diagnostic (bench.py roofline): restrict the BF16 knerf_mlp_backward of the calling thread to its dgrad
+ * kernel (mask 1), its weight-gradient kernel (mask 2) or both (3, default) so they can be timed apart.  */
+int knerf_debug_backward_parts(int mask);
+
 int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
                         void* stream);
 

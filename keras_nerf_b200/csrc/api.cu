@@ -79,6 +79,11 @@ extern "C" int knerf_device_supports_bf16(void) {
   return (prop.major == 10 && tc_path_compiled()) ? 1 : 0;
 }
 
+extern "C" int knerf_debug_backward_parts(int mask) {
+  tc_set_backward_parts(mask);
+  return KNERF_OK;
+}
+
 extern "C" int64_t knerf_param_count(const knerf_config* cfg) {
   Model m;
   if (build_model(cfg, &m) != KNERF_OK) return -1;

@@ -15,4 +15,6 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, cudaStream_t st);
 
+void tc_set_backward_parts(int mask);
+
 }  // namespace knerf

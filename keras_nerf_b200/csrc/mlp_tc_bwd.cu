@@ -427,6 +427,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 
 }  // namespace
 
+// diagnostic: which of the two backward kernels knerf_mlp_backward launches in BF16 mode (bit 0 dgrad, bit 1 wgrad)
+static thread_local int g_bwd_parts = 3;
+void tc_set_backward_parts(int mask) { g_bwd_parts = mask & 3; }
+
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
   (void)params;
@@ -442,7 +446,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   uint8_t* dz = rec + n_tiles * (int64_t)kRecBytes;
   const TcParams P = tc_make_params(m);
 
-  {
+  if (g_bwd_parts & 1) {
     const int64_t n_pairs = cdiv(n_tiles, 2);
     const int grid = (int)std::min<int64_t>(n_pairs, kNumSMs);
     const size_t smem = sizeof(ChainSmem);
@@ -450,7 +454,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     tc_mlp_dgrad_kernel<<<grid, kThreads, smem, st>>>((const uint8_t*)packed, (const float4*)d_pre, M, rec, dz, grads, P);
     KN_LAUNCH_CHECK();
   }
-  {
+  if (g_bwd_parts & 2) {
     static const WTaskTable h_table = build_task_table();   // ~3 KB, passed by value as a __grid_constant__
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(26, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
