@@ -199,6 +199,10 @@ int knerf_debug_backward_parts(int mask);
 int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
                         void* stream);
 
+/* Same for one tcgen05.mma.cta_group::2 tile pair: D[256,N] = A[256,K] * B[N,K]^T, a_blob = [2][K/8][128][8],
+ * b_blob = [2][K/8][N/2][8] (CTA c of the pair owns A rows 128c.. and B rows c*N/2..).                      */
+int knerf_selftest_umma2(const void* a_blob, const void* b_blob, int N, int K, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "knerf_mse": (_I, [_P, _P, _L, _P, _P]),
     "knerf_debug_backward_parts": (_I, [_I]),
     "knerf_selftest_umma": (_I, [_I, _P, _P, _I, _I, _P, _P]),
+    "knerf_selftest_umma2": (_I, [_P, _P, _I, _I, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

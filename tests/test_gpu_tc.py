@@ -203,3 +203,21 @@ def test_tc_train_step_tracks_fp32():
         assert b["fine_loss"] == pytest.approx(a["fine_loss"], rel=2e-2)
         assert b["coarse_psnr"] == pytest.approx(a["coarse_psnr"], abs=0.1)
     assert logs["bf16"][2]["coarse_loss"] < logs["bf16"][0]["coarse_loss"]
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (128, 32), (256, 256), (64, 16)])
+def test_umma_selftest_2cta(N, K):
+    """one tcgen05.mma.cta_group::2 tile pair (M = 256 across two SMs, B split by N)"""
+    from keras_nerf_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N * 7 + K)
+    A = torch.randn(256, K, generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    a_d = torch.stack([kmajor_blob(A[:128]), kmajor_blob(A[128:])]).contiguous().to(dev)
+    b_d = torch.stack([kmajor_blob(B[:N // 2]), kmajor_blob(B[N // 2:])]).contiguous().to(dev)
+    out = torch.full((256, N), float("nan"), device=dev)
+    _lib.call("knerf_selftest_umma2", a_d.data_ptr(), b_d.data_ptr(), N, K, _lib.ptr(out), _lib.stream())
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().T
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= 1e-3 * max(1.0, float(ref.abs().max())), err
