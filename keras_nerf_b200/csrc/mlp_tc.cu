@@ -17,7 +17,11 @@
 // Shared memory: 2 x 64 KB hidden activations + 2 x 16 KB encodings + 4 x 16 KB weight stages = 224 KB.
 #include "mlp_tc.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "tc_roles.cuh"
+#include "tc_roles2.cuh"
 
 namespace knerf {
 using namespace tc;
@@ -162,22 +166,38 @@ __device__ __forceinline__ void copy_smem_to_global(const uint8_t* src, uint8_t*
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
-template <bool TRAIN>
+// TWO = false: one CTA per SM works alone (cta_group::1).  TWO = true: launched as clusters of 2, the CTA pair
+// shares every weight stage through cta_group::2 MMAs (tc_roles2.cuh); a work unit is then four tiles.
+template <bool TRAIN, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o, const float* __restrict__ d,
                   const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
                   uint8_t* __restrict__ rec) {
+  using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t n_pairs = (n_tiles + 1) / 2;
-  const uint32_t tmem = chain_setup(sm, tid, warp);
+  constexpr int kTilesPerUnit = TWO ? 4 : 2;
+  const int64_t n_pairs = (n_tiles + kTilesPerUnit - 1) / kTilesPerUnit;   // work units (tile pairs / quads)
+  const uint32_t cta = TWO ? cluster_ctarank() : 0u;
+  const int64_t first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
+  uint32_t tmem;
+  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp); else tmem = chain_setup(sm, tid, warp);
 
   if (warp == 0) {
-    if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
+    if constexpr (TWO) {
+      if (lane == 0) producer2_role<FwdProg>(sm, packed, cta, n_pairs, first, stride);
+    } else {
+      if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
+    }
   } else if (warp == 1) {
-    if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
+    if constexpr (TWO) {
+      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, n_pairs, first, stride);
+      else if (lane == 0) relay_role<FwdProg>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
+    } else {
+      if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
+    }
   } else {
     // =========================== compute warps ==========================
     const int q = warp & 3, h = (warp - 2) >> 2;
@@ -188,32 +208,44 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     uint32_t acc_par[2] = {0, 0};
     float sig_keep0 = 0.f, sig_keep1 = 0.f;   // sigma of this thread's row, per tile slot
 
+    auto tile_of = [&](int64_t unit, int tl) -> int64_t {
+      return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
+    };
+    auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand is in smem
+      if constexpr (TWO) {
+        a_ready_arrive2(sm, tl, lane);
+      } else {
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(&sm.a_ready[tl]);
+      }
+    };
     auto prologue = [&](int64_t pair, int tl) {
-      const int64_t tile = pair * 2 + tl;
+      const int64_t tile = tile_of(pair, tl);
       const int64_t g = tile * kTileM + r;
       pe_xyz(sm.xs[tl], r, h, g < M, o, d, t, g, S);
       if (TRAIN && tile < n_tiles) {
         named_bar_sync(1, kComputeThreads);
         copy_smem_to_global(sm.xs[tl], rec + tile * kRecBytes + kRecXS, kXSBytes, ctid);
       }
-      fence_async_smem();
-      mbar_arrive(&sm.a_ready[tl]);
+      a_ready_arrive(tl);
     };
 
-    if ((int64_t)blockIdx.x < n_pairs) {
+    if (first < n_pairs) {
 #pragma unroll 1
-      for (int tl = 0; tl < 2; ++tl) prologue(blockIdx.x, tl);
+      for (int tl = 0; tl < 2; ++tl) prologue(first, tl);
     }
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = first; pair < n_pairs; pair += stride) {
       for (int s = 0; s < FwdProg::kSteps; ++s) {
 #pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
-          const int64_t tile = pair * 2 + tl;
+          const int64_t tile = tile_of(pair, tl);
           const int64_t g = tile * kTileM + r;
           const bool valid = g < M;
           const bool save = TRAIN && tile < n_tiles;
           uint8_t* rec_t = rec + tile * kRecBytes;
-          mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
+          if constexpr (TWO) mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
+          else mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
 
@@ -276,9 +308,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                   *reinterpret_cast<uint4*>(rec_t + kRecDS + 8192 + i) = make_uint4(0, 0, 0, 0);
               }
             }
-            tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(&sm.a_ready[tl]);
+            a_ready_arrive(tl);
           } else {
             // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
             const float* wrgb = aux + 13 * 256;
@@ -322,14 +352,14 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             named_bar_sync(1, kComputeThreads);
             tc_fence_before();
             // this tile is finished: start the next pair's tile in the same slot right away
-            const int64_t next = pair + gridDim.x;
+            const int64_t next = pair + stride;
             if (next < n_pairs) prologue(next, tl);
           }
         }
       }
     }
   }
-  chain_teardown(tmem, warp);
+  if constexpr (TWO) chain2_teardown(tmem, warp); else chain_teardown(tmem, warp);
 }
 
 }  // namespace
@@ -369,18 +399,43 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
                "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");
-  const int64_t n_pairs = cdiv(cdiv(M, kTileM), 2);
-  const int grid = (int)std::min<int64_t>(n_pairs, kNumSMs);
-  const size_t smem = sizeof(ChainSmem);
-  if (training) {
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mlp_fwd_kernel<true><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S, (float4*)rgbsigma,
-                                                          (uint8_t*)ws);
+  const int64_t n_tiles = cdiv(M, kTileM);
+  // Experimental: KNERF_TC_2CTA=1 selects the cta_group::2 variant (CTA pairs share every weight stage).  It is
+  // bit-identical but measured SLOWER on B200 (457 vs 999 TFLOP/s): with only two tiles in flight per CTA the
+  // cross-CTA barrier round trips (relay of "stage landed", remote "A ready" arrives, multicast commits) sit on
+  // the critical path.  Kept for the next round (needs .cta_group::2 tensor-map TMA to drop the relay).
+  static const bool want_two = std::getenv("KNERF_TC_2CTA") != nullptr;
+  const bool two = want_two && n_tiles >= 4;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = st;
+  if (two) {
+    const int64_t n_quads = cdiv(n_tiles, 4);
+    cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(n_quads, kNumSMs / 2)));
+    cfg.dynamicSmemBytes = sizeof(Chain2Smem);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
   } else {
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mlp_fwd_kernel<false><<<grid, kThreads, smem, st>>>((const uint8_t*)packed, o, d, t, M, S, (float4*)rgbsigma,
-                                                           nullptr);
+    cfg.gridDim = dim3((unsigned)std::min<int64_t>(cdiv(n_tiles, 2), kNumSMs));
+    cfg.dynamicSmemBytes = sizeof(ChainSmem);
   }
+  const uint8_t* pk = (const uint8_t*)packed;
+  float4* out = (float4*)rgbsigma;
+  uint8_t* rec = training ? (uint8_t*)ws : nullptr;
+#define KN_LAUNCH_FWD(TR, TW)                                                                                       \
+  do {                                                                                                              \
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<TR, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                 (int)cfg.dynamicSmemBytes));                                                       \
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<TR, TW>, pk, o, d, t, M, S, out, rec));                       \
+  } while (0)
+  if (training && two) KN_LAUNCH_FWD(true, true);
+  else if (training) KN_LAUNCH_FWD(true, false);
+  else if (two) KN_LAUNCH_FWD(false, true);
+  else KN_LAUNCH_FWD(false, false);
+#undef KN_LAUNCH_FWD
   KN_LAUNCH_CHECK();
   return KNERF_OK;
 }
