@@ -1,0 +1,110 @@
+"""GPU (-m gpu): the reference-facing class API around the hot path -- compile-time checks, test_step, fit loop,
+checkpoint round trip (keras_nerf/model/nerf/nerf.py:45-136,475-497; train_single.py:137-148)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(precision="fp32", **kw):
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    g = load_golden("model")
+    mlp_mod.set_seed(42)
+    m = K.NeRF(precision=precision, **kw)
+    m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=16, image_width=16, ray_chunks=128,
+              white_background=True)
+    rays = (g["o"][None], g["d"][None], g["t"][None])
+    return K, g, m, rays
+
+
+def test_compile_checks_like_reference():
+    import keras_nerf_b200 as K
+    m = K.NeRF()
+    with pytest.raises(AssertionError):        # nerf.py:100: ray_chunks must divide the number of rays
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=10, image_width=10, ray_chunks=33)
+    m2 = K.NeRF()
+    m2.compile(optimizer="adam", loss="mse", batch_size=1, image_height=4, image_width=4, ray_chunks=4096)
+    assert m2.ray_chunks == 16 and m2.sequential_chunks == 1      # nerf.py:95-98 clamps to num_rays
+    assert m2.coarse.count_params() == 595844 and len(m2.fine.trainable_variables) == 24
+    with pytest.raises(NotImplementedError):
+        K.NeRF().compile(optimizer="sgd", loss="mse", batch_size=1, image_height=4, image_width=4, ray_chunks=16)
+
+
+def test_test_step_matches_oracle_losses():
+    K, g, m, rays = _setup()
+    logs = m.test_step((g["images"], rays), u_fine=g["u_fine"])
+    cfg = O.NerfConfig()
+    rng = np.random.default_rng(42)
+    pc, pf = O.init_params(cfg, rng), O.init_params(cfg, rng)
+    orays = tuple(torch.from_numpy(np.asarray(r)) for r in rays)
+    c, f = O.predict_and_render_images(pc, pf, cfg, orays, g["u_fine"], 128, True)
+    tgt = torch.from_numpy(g["images"][..., :3])
+    assert logs["coarse_loss"] == pytest.approx(float(O.mse(tgt, c["image"])), rel=1e-5)
+    assert logs["fine_loss"] == pytest.approx(float(O.mse(tgt, f["image"])), rel=5e-3)
+    assert logs["coarse_psnr"] == pytest.approx(float(O.psnr(tgt, c["image"]).mean()), abs=1e-3)
+    assert set(logs) == {"coarse_loss", "coarse_psnr", "coarse_ssim", "fine_loss", "fine_psnr", "fine_ssim"}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fit_reduces_loss_and_checkpoint_round_trip(precision, tmp_path):
+    K, g, m, rays = _setup(precision)
+    # a learnable target: the analytic sphere of the synthetic scene instead of noise
+    from keras_nerf_b200.data.synthetic import analytic_rgba
+    img = analytic_rgba(torch.from_numpy(g["o"]).cuda(), torch.from_numpy(g["d"]).cuda(), True)[None]
+    seen = []
+
+    class Monitor:   # the two hooks NeRFTrainMonitor uses (callback.py:62,113)
+        def on_train_batch_end(self, step, logs):
+            seen.append(("batch", step))
+
+        def on_epoch_end(self, epoch, logs):
+            seen.append(("epoch", epoch, logs["fine_loss"]))
+
+    hist = m.fit([(img, rays)] * 2, epochs=4, validation_data=[(img, rays)], callbacks=[Monitor()], verbose=0)
+    assert len(hist["coarse_loss"]) == 4 and "val_fine_psnr" in hist
+    assert hist["coarse_loss"][-1] < hist["coarse_loss"][0]
+    assert [s for s in seen if s[0] == "epoch"][-1][1] == 3 and ("batch", 1) in seen
+    # save_model / load_model (nerf.py:45-76,132-136): config json + per-net weights, Keras [in,out] layout
+    path = str(tmp_path / "model")
+    m.save_model(path)
+    cfg = json.load(open(os.path.join(path, "model_config.json")))
+    assert cfg == {"n_coarse": 64, "n_fine": 128, "pos_emb_xyz": 10, "pos_emb_dir": 4, "n_layers": 8,
+                   "dense_units": 256, "skip_layer": 4}
+    m2 = K.NeRF(model_path=path, precision=precision)
+    m2.compile(optimizer="adam", loss="mse", batch_size=1, image_height=16, image_width=16, ray_chunks=256,
+               white_background=True, is_training=False)
+    assert torch.equal(m2.coarse.params, m.coarse.params) and torch.equal(m2.fine.params, m.fine.params)
+    a = m.predict_and_render_images(rays, u_fine=g["u_fine"])[1]["image"]
+    b = m2.predict_and_render_images(rays, u_fine=g["u_fine"])[1]["image"]
+    assert float((a - b).abs().max()) <= 1e-6
+    w = m2.coarse.get_weights()
+    assert w[0].shape == (63, 256) and w[1].shape == (256,) and w[10].shape == (319, 256) and w[-2].shape == (128, 3)
+
+
+def test_rays_generator_feeds_model_like_inference_script():
+    """inference.py:61-114: orbit poses -> RaysGenerator -> predict_and_render_images -> frames"""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    mlp_mod.set_seed(42)
+    m = K.NeRF(precision="bf16")
+    wh = 32
+    m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=wh, image_width=wh, ray_chunks=512,
+              white_background=True, is_training=False)
+    gen = K.RaysGenerator(K.get_focal_from_fov(0.6911112070083618, wh), wh, wh, 2.0, 6.0, m.n_coarse)
+    frames = []
+    for theta in range(0, 360, 120):
+        o, d, t = gen(K.pose_spherical(float(theta), -30.0, 4.0))
+        _, fine = m.predict_and_render_images((o[None], d[None], t[None]))
+        frames.append(fine["image"][0])
+        assert fine["image"].shape == (1, wh, wh, 3) and fine["depth"].shape == (1, wh, wh)
+        assert fine["weights"].shape == (1, wh, wh, 192)
+        assert float(fine["image"].min()) >= 0.0 and float(fine["image"].max()) <= 1.0
+    assert not torch.equal(frames[0], frames[1])
