@@ -196,6 +196,15 @@ int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* strea
  * kernel (mask 1), its weight-gradient kernel (mask 2) or both (3, default) so they can be timed apart.  */
 int knerf_debug_backward_parts(int mask);
 
+/* Diagnostic / A-B measurements: which BF16 chain kernels run.  0 = default (CTA pairs, cta_group::2 MMAs;
+ * KNERF_TC_2CTA=0 in the environment selects single CTAs), 1 = single-CTA kernels, 2 = CTA pairs.          */
+int knerf_debug_tc_variant(int variant);
+
+/* Diagnostic: per-CTA clock64() counters of the BF16 forward kernel (40 uint64 per CTA; slots documented in
+ * csrc/tc_roles.cuh), copied to host_out and cleared.  Returns the number of values written; 0 unless the
+ * library was built with -DKNERF_TC_TIMING (release builds carry no instrumentation).                      */
+int knerf_debug_tc_timing(unsigned long long* host_out, int n);
+
 int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
                         void* stream);
 

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libknerf.so")
+# KNERF_LIB_PATH: diagnostics only (e.g. a -DKNERF_TC_TIMING build kept next to the release library)
+LIB_PATH = os.environ.get("KNERF_LIB_PATH") or os.path.join(_HERE, "lib", "libknerf.so")
 
 OOB_ZERO, OOB_CLAMP, OOB_COUNT = 0, 1, 2
 SCAN_SEQUENTIAL = 0x10   # OR-ed into oob_mode: pdf/cdf summed left to right (TF-CPU / NumPy order)
@@ -61,6 +62,8 @@ SIGNATURES = {
     "knerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _I, _P]),
     "knerf_mse": (_I, [_P, _P, _L, _P, _P]),
     "knerf_debug_backward_parts": (_I, [_I]),
+    "knerf_debug_tc_timing": (_I, [_P, _I]),
+    "knerf_debug_tc_variant": (_I, [_I]),
     "knerf_selftest_umma": (_I, [_I, _P, _P, _I, _I, _P, _P]),
     "knerf_selftest_umma2": (_I, [_P, _P, _I, _I, _P, _P]),
 }

@@ -84,6 +84,13 @@ extern "C" int knerf_debug_backward_parts(int mask) {
   return KNERF_OK;
 }
 
+extern "C" int knerf_debug_tc_variant(int variant) {
+  tc_set_variant(variant <= 0 ? -1 : variant);
+  return KNERF_OK;
+}
+
+extern "C" int knerf_debug_tc_timing(unsigned long long* host_out, int n) { return tc_debug_timing(host_out, n); }
+
 extern "C" int64_t knerf_param_count(const knerf_config* cfg) {
   Model m;
   if (build_model(cfg, &m) != KNERF_OK) return -1;

@@ -30,6 +30,52 @@ using namespace tcl;
 namespace {
 
 // ---- weight packing --------------------------------------------------------------------------------------
+// B operand element of forward step s at reduction index k (hs part first, then the encoding part) and output n
+__device__ __forceinline__ float fwd_weight(const float* __restrict__ params, const TcParams& P, int s, int k, int n) {
+  const int L = FwdProg::layer(s), N = FwdProg::N(s), kh = FwdProg::nk_h(s) * kKStage;
+  const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : (L == 10) ? 283 : 256;
+  const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
+  return row < fan_in ? params[P.w_off[L] + (int64_t)row * N + n] : 0.f;
+}
+// B operand element of dgrad step b: W[n][k] (n = input feature < 256, k = output feature)
+__device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P, int b, int k, int n) {
+  return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * BwdProg::ld(b) + k];
+}
+
+template <class Prog, bool FWD>
+__device__ __forceinline__ void pack_pair(const float* __restrict__ params, const TcParams& P,
+                                          uint8_t* __restrict__ blob, int gtid, int gsz) {
+  using PL = PairLayout<Prog>;
+  for (int v = gtid; v < PL::kBytes / 16; v += gsz) {
+    const int byte = v * 16;
+    int s = 0;
+    while (s + 1 < Prog::kSteps && byte >= PL::blob_off(s + 1)) ++s;
+    const int local = byte - PL::blob_off(s);
+    const int N = Prog::N(s), half = N / 2, ktot = PL::ktot(s);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (local < 2 * N * ktot) {
+      const int i = local / (2 * N * kPairK);                 // stage
+      const int rem = local - i * (2 * N * kPairK);
+      const int pb = PL::piece_bytes(s, i);
+      const int cta = rem / pb, r2 = rem - cta * pb;
+      const int c = r2 / (half * 16), nl = (r2 - c * half * 16) / 16;
+      const int k0 = i * kPairK + c * 8, n = cta * half + nl;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = FWD ? fwd_weight(params, P, s, k0 + 2 * e, n) : bwd_weight(params, P, s, k0 + 2 * e, n);
+        const float b = FWD ? fwd_weight(params, P, s, k0 + 2 * e + 1, n) : bwd_weight(params, P, s, k0 + 2 * e + 1, n);
+        w[e] = pack_bf16x2(a, b);
+      }
+    } else {   // bias piece [2 chunks][N/2][8]: k = 15 <- bias[n]
+      const int rem = local - 2 * N * ktot, pb = 16 * N;
+      const int cta = rem / pb, r2 = rem - cta * pb;
+      const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
+      if (cb == 1) w[3] = pack_bf16x2(0.f, params[P.b_off[Prog::layer(s)] + cta * half + nl]);
+    }
+    *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // forward blob: per step, per K stage: [4 chunks][N][8], element (c, n, e) = W[row(ks, c, e)][n]   (W^T, K-major)
 // dgrad blob:   per step, per K stage: [4 chunks][256][8], element (c, n, e) = W[n][ks*32 + c*8 + e] (W, K-major)
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, TcParams P,
@@ -77,6 +123,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
     *reinterpret_cast<uint4*>(packed + kBwdBlobOff + byte) =
         make_uint4(pack_bf16x2(W[0], W[1]), pack_bf16x2(W[2], W[3]), pack_bf16x2(W[4], W[5]), pack_bf16x2(W[6], W[7]));
   }
+  // pair (cta_group::2) blobs: same weights, K = 64 stages, one contiguous piece per (stage, CTA)
+  pack_pair<FwdProg, true>(params, P, packed + kFwdPairOff, gtid, gsz);
+  pack_pair<BwdProg, false>(params, P, packed + kBwdPairOff, gtid, gsz);
   float* aux = reinterpret_cast<float*>(packed + kAuxOff);
   for (int i = gtid; i < kAuxFloats; i += gsz) {
     const int blk = i >> 8, j = i & 255;
@@ -95,14 +144,40 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
 }
 
 // ---- positional encoding into an A operand -----------------------------------------------------------------
-// thread (row r, half h) of the 256 compute threads; element (row, col) of a [128 x K] chunk-major operand
-__device__ __forceinline__ void store_elem(uint8_t* base, int r, int col, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(base + (col >> 3) * kChunkA + r * 16 + (col & 7) * 2) = __float2bfloat16_rn(v);
+// thread (row r, half h) of the 256 compute threads builds 32 consecutive columns of its row in registers and
+// writes them as four 16-byte vectors (512 contiguous bytes per warp and chunk: conflict-free), to the smem
+// operand and -- when training -- to the tile's record in HBM.
+//
+// sin/cos(2^f x): ONE accurate sincosf per coordinate at the half's base frequency (|arg| <= ~100: fast path),
+// then angle doubling  sin 2a = 2 sin a cos a,  cos 2a = 1 - 2 sin^2 a.  The absolute error doubles per step
+// (<= 32 x 6e-8 after five), far below the bf16 rounding of the operand (2^-9 relative).
+__device__ __forceinline__ void angle_double(float (&sn)[3], float (&cs)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s2 = 2.f * sn[c] * cs[c];
+    cs[c] = fmaf(-2.f * sn[c], sn[c], 1.f);
+    sn[c] = s2;
+  }
 }
 
-// PE_10(o + d t) -> 63 columns (+ zero pad column 63): h=0 writes identity + frequencies 0..4, h=1 5..9
-__device__ __noinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ o,
-                                       const float* __restrict__ d, const float* __restrict__ t, int64_t g, int S) {
+__device__ __forceinline__ void store_cols(uint8_t* xs, uint8_t* rec, int r, int chunk0, const float* v, int nchunks) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nchunks) {
+      const uint4 pk = make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                                  pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+      const int off = (chunk0 + k) * kChunkA + r * 16;
+      *reinterpret_cast<uint4*>(xs + off) = pk;
+      if (rec) *reinterpret_cast<uint4*>(rec + off) = pk;
+    }
+  }
+}
+
+// PE_10(o + d t) -> 63 columns + the constant-1 column 63 (carries the folded bias, tc_layout.cuh).
+// Column order (utils.py:176-186): x y z, then per frequency f: sin(2^f xyz), cos(2^f xyz).
+// h = 0: columns 0..31 (identity, f = 0..3, f = 4 up to cos y);  h = 1: columns 32..63 (cos(2^4 z), f = 5..9, 1).
+__device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, bool valid, const float* __restrict__ o,
+                                    const float* __restrict__ d, const float* __restrict__ t, int64_t g, int S) {
   float p[3] = {0.f, 0.f, 0.f};
   if (valid) {
     const int64_t ray = g / S;
@@ -110,59 +185,69 @@ __device__ __noinline__ void pe_xyz(uint8_t* xs, int r, int h, bool valid, const
 #pragma unroll
     for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(__ldg(o + ray * 3 + c), __fmul_rn(__ldg(d + ray * 3 + c), tt));
   }
+  float sn[3], cs[3], v[34];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sincosf(ldexpf(p[c], 4 * h), &sn[c], &cs[c]);
   if (h == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) store_elem(xs, r, c, p[c]);
-  } else {
-    store_elem(xs, r, 63, 1.f);   // constant-1 column: carries the folded bias (tc_layout.cuh)
-  }
-#pragma unroll 1
-  for (int i = 0; i < 5; ++i) {
-    const int f = h * 5 + i;
+    for (int c = 0; c < 3; ++c) v[c] = p[c];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float sn, cs;
-      sincosf(ldexpf(p[c], f), &sn, &cs);     // accurate range reduction: |arg| reaches ~3e3
-      store_elem(xs, r, 3 + 6 * f + c, sn);
-      store_elem(xs, r, 3 + 6 * f + 3 + c, cs);
+    for (int i = 0; i < 5; ++i) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { v[3 + 6 * i + c] = sn[c]; v[6 + 6 * i + c] = cs[c]; }   // v[32] = cos(2^4 z): h = 1's
+      angle_double(sn, cs);
     }
+  } else {
+    v[0] = cs[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      angle_double(sn, cs);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { v[1 + 6 * i + c] = sn[c]; v[4 + 6 * i + c] = cs[c]; }
+    }
+    v[31] = 1.f;
   }
+  store_cols(xs, rec, r, 4 * h, v, 4);
 }
 
-// PE_4(d) -> 27 columns (+ zero pad 27..31) into chunks 0..3 of the xs buffer; h=0: identity + f 0,1; h=1: f 2,3
-__device__ __noinline__ void pe_dir(uint8_t* xs, int r, int h, bool valid, const float* __restrict__ d, int64_t g,
-                                       int S) {
-  float v[3] = {0.f, 0.f, 0.f};
+// PE_4(d) -> 27 columns, zeros in 27..30, the constant-1 column 31 (folded bias of steps 6..9) into chunks 0..3
+// of the xs buffer.  h = 0: columns 0..15 (identity, f = 0, 1, sin(4 x));  h = 1: columns 16..31.
+// The record keeps 8 chunks for this operand (one 32 KB weight-gradient unit): chunks 4..7 are written as zeros.
+__device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, bool valid, const float* __restrict__ d,
+                                    int64_t g, int S) {
+  float x[3] = {0.f, 0.f, 0.f};
   if (valid) {
     const int64_t ray = g / S;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = __ldg(d + ray * 3 + c);
+    for (int c = 0; c < 3; ++c) x[c] = __ldg(d + ray * 3 + c);
   }
+  float sn[3], cs[3], v[18];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sincosf(ldexpf(x[c], 2 * h), &sn[c], &cs[c]);
   if (h == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) store_elem(xs, r, c, v[c]);
-  } else {
+    for (int c = 0; c < 3; ++c) v[c] = x[c];
 #pragma unroll
-    for (int c = 27; c < 31; ++c) store_elem(xs, r, c, 0.f);
-    store_elem(xs, r, 31, 1.f);   // constant-1 column for the folded bias of steps 6..9
-  }
-#pragma unroll 1
-  for (int i = 0; i < 2; ++i) {
-    const int f = h * 2 + i;
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float sn, cs;
-      sincosf(ldexpf(v[c], f), &sn, &cs);
-      store_elem(xs, r, 3 + 6 * f + c, sn);
-      store_elem(xs, r, 3 + 6 * f + 3 + c, cs);
+      for (int c = 0; c < 3; ++c) { v[3 + 6 * i + c] = sn[c]; v[6 + 6 * i + c] = cs[c]; }
+      angle_double(sn, cs);
     }
+    v[15] = sn[0];
+  } else {
+    v[0] = sn[1]; v[1] = sn[2]; v[2] = cs[0]; v[3] = cs[1]; v[4] = cs[2];
+    angle_double(sn, cs);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { v[5 + c] = sn[c]; v[8 + c] = cs[c]; }
+    v[11] = v[12] = v[13] = v[14] = 0.f;
+    v[15] = 1.f;
   }
-}
-
-// copy `bytes` of a smem operand image to global (all 256 compute threads, 16 B vectors)
-__device__ __forceinline__ void copy_smem_to_global(const uint8_t* src, uint8_t* dst, int bytes, int ctid) {
-  for (int i = ctid * 16; i < bytes; i += kComputeThreads * 16)
-    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+  store_cols(xs, rec, r, 2 * h, v, 2);
+  if (rec) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      *reinterpret_cast<uint4*>(rec + (4 + 2 * h + k) * kChunkA + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
@@ -183,11 +268,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
   const uint32_t cta = TWO ? cluster_ctarank() : 0u;
   const int64_t first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
   uint32_t tmem;
-  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp); else tmem = chain_setup(sm, tid, warp);
+  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp, cta); else tmem = chain_setup(sm, tid, warp);
 
   if (warp == 0) {
     if constexpr (TWO) {
-      if (lane == 0) producer2_role<FwdProg>(sm, packed, cta, n_pairs, first, stride);
+      if (lane == 0) producer2_role<FwdProg>(sm, packed + kFwdPairOff, cta, n_pairs, first, stride);
     } else {
       if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
     }
@@ -202,7 +287,6 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     // =========================== compute warps ==========================
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int ctid = tid - 64;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
@@ -223,14 +307,12 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     auto prologue = [&](int64_t pair, int tl) {
       const int64_t tile = tile_of(pair, tl);
       const int64_t g = tile * kTileM + r;
-      pe_xyz(sm.xs[tl], r, h, g < M, o, d, t, g, S);
-      if (TRAIN && tile < n_tiles) {
-        named_bar_sync(1, kComputeThreads);
-        copy_smem_to_global(sm.xs[tl], rec + tile * kRecBytes + kRecXS, kXSBytes, ctid);
-      }
+      pe_xyz(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRecBytes + kRecXS : nullptr, r, h, g < M, o, d, t, g, S);
       a_ready_arrive(tl);
     };
 
+    KN_PROF_DECL();
+    KN_PROF_BEGIN(t_c);
     if (first < n_pairs) {
 #pragma unroll 1
       for (int tl = 0; tl < 2; ++tl) prologue(first, tl);
@@ -244,8 +326,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           const bool valid = g < M;
           const bool save = TRAIN && tile < n_tiles;
           uint8_t* rec_t = rec + tile * kRecBytes;
+          KN_PROF_BEGIN(t_w);
           if constexpr (TWO) mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
           else mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
+          KN_PROF_END(t_w, 4);
+          KN_PROF_BEGIN(t_e);
           acc_par[tl] ^= 1;
           tc_fence_after();
 
@@ -300,13 +385,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             }
             if (s == 5) {
               // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for rgb_features
-              pe_dir(sm.xs[tl], r, h, valid, d, g, S);
-              if (save) {
-                named_bar_sync(1, kComputeThreads);
-                copy_smem_to_global(sm.xs[tl], rec_t + kRecDS, 8192, ctid);
-                for (int i = ctid * 16; i < 8192; i += kComputeThreads * 16)
-                  *reinterpret_cast<uint4*>(rec_t + kRecDS + 8192 + i) = make_uint4(0, 0, 0, 0);
-              }
+              pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, valid, d, g, S);
             }
             a_ready_arrive(tl);
           } else {
@@ -355,9 +434,12 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             const int64_t next = pair + stride;
             if (next < n_pairs) prologue(next, tl);
           }
+          KN_PROF_END(t_e, 6 + tl * 16 + s);
         }
       }
     }
+    KN_PROF_END(t_c, 5);
+    if (tid == 64) { KN_PROF_FLUSH(); }
   }
   if constexpr (TWO) chain2_teardown(tmem, warp); else chain_teardown(tmem, warp);
 }
@@ -365,6 +447,32 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 }  // namespace
 
 bool tc_path_compiled() { return true; }
+
+// Which chain-kernel variant runs: CTA pairs (cta_group::2, default) or single CTAs.  KNERF_TC_2CTA=0 in the
+// environment or knerf_debug_tc_variant(1) selects the single-CTA kernels (kept for A/B measurements and tests).
+static int g_tc_variant = -1;
+void tc_set_variant(int v) { g_tc_variant = v; }
+bool tc_use_pairs() {
+  if (g_tc_variant < 0) {
+    const char* e = std::getenv("KNERF_TC_2CTA");
+    g_tc_variant = (e != nullptr && e[0] == '0') ? 1 : 2;
+  }
+  return g_tc_variant == 2;
+}
+
+// diagnostic (-DKNERF_TC_TIMING builds only): copy and clear the forward kernel's per-CTA cycle counters
+int tc_debug_timing(unsigned long long* host_out, int n) {
+#ifdef KNERF_TC_TIMING
+  static unsigned long long zeros[160 * 40];
+  if (n > 160 * 40) n = 160 * 40;
+  if (cudaMemcpyFromSymbol(host_out, g_tc_prof, (size_t)n * 8) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tc_prof, zeros, sizeof(zeros)) != cudaSuccess) return -1;
+  return n;
+#else
+  (void)host_out; (void)n;
+  return 0;
+#endif
+}
 
 int64_t tc_packed_weight_bytes(const Model& m) { return is_flagship(m) ? kPackedBytes : -1; }
 
@@ -400,12 +508,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
                    (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
                "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");
   const int64_t n_tiles = cdiv(M, kTileM);
-  // Experimental: KNERF_TC_2CTA=1 selects the cta_group::2 variant (CTA pairs share every weight stage).  It is
-  // bit-identical but measured SLOWER on B200 (457 vs 999 TFLOP/s): with only two tiles in flight per CTA the
-  // cross-CTA barrier round trips (relay of "stage landed", remote "A ready" arrives, multicast commits) sit on
-  // the critical path.  Kept for the next round (needs .cta_group::2 tensor-map TMA to drop the relay).
-  static const bool want_two = std::getenv("KNERF_TC_2CTA") != nullptr;
-  const bool two = want_two && n_tiles >= 4;
+  const bool two = tc_use_pairs() && n_tiles >= 4;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);

@@ -10,7 +10,10 @@
 //     blobs are consumed as MN-major UMMA operands (same bytes, other axis; see tc_ptx.cuh), fp32 partial
 //     sums stay in TMEM across all tiles of a work item and are flushed once with red.global.add.f32.
 #include "mlp_tc.cuh"
+#include <type_traits>
+
 #include "tc_roles.cuh"
+#include "tc_roles2.cuh"
 
 namespace knerf {
 using namespace tc;
@@ -23,21 +26,50 @@ namespace {
 // =============================================================================================================
 // dgrad chain
 // =============================================================================================================
+// TWO = false: one CTA per SM works alone.  TWO = true: clusters of 2, cta_group::2 MMAs (tc_roles2.cuh); a work
+// unit is then four tiles (two per CTA).
+template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict__ d_pre, int64_t M,
                     const uint8_t* __restrict__ rec, uint8_t* __restrict__ dz, float* __restrict__ grads, TcParams P) {
+  using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  const int64_t n_pairs = (n_tiles + 1) / 2;
-  const uint32_t tmem = chain_setup(sm, tid, warp);
+  constexpr int kTilesPerUnit = TWO ? 4 : 2;
+  const int64_t n_pairs = (n_tiles + kTilesPerUnit - 1) / kTilesPerUnit;   // work units (tile pairs / quads)
+  const uint32_t cta = TWO ? cluster_ctarank() : 0u;
+  const int64_t first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
+  uint32_t tmem;
+  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp, cta); else tmem = chain_setup(sm, tid, warp);
 
   if (warp == 0) {
-    if (lane == 0) producer_role<BwdProg>(sm, packed + kBwdBlobOff, n_pairs);
+    if constexpr (TWO) {
+      if (lane == 0) producer2_role<BwdProg>(sm, packed + kBwdPairOff, cta, n_pairs, first, stride);
+    } else {
+      if (lane == 0) producer_role<BwdProg>(sm, packed + kBwdBlobOff, n_pairs);
+    }
   } else if (warp == 1) {
-    if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
+    if constexpr (TWO) {
+      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, n_pairs, first, stride);
+      else if (lane == 0) relay_role<BwdProg>(sm, n_pairs, first, stride);
+    } else {
+      if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
+    }
   } else {
+    auto tile_of = [&](int64_t unit, int tl) -> int64_t {
+      return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
+    };
+    auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand is in smem
+      if constexpr (TWO) {
+        a_ready_arrive2(sm, tl, lane);
+      } else {
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(&sm.a_ready[tl]);
+      }
+    };
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -49,7 +81,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
 
     // tile start: dG = d(rgb_pre) Wc^T (K = 3, CUDA cores) becomes the first A operand
     auto prologue = [&](int64_t pair, int tl) {
-      const int64_t tile = pair * 2 + tl;
+      const int64_t tile = tile_of(pair, tl);
       const int64_t g = tile * kTileM + r;
       const bool active = tile < n_tiles;
       float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -83,20 +115,19 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
         *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
         if (active) *reinterpret_cast<uint4*>(dz_t + kDzG + off) = pk;
       }
-      fence_async_smem();
-      mbar_arrive(&sm.a_ready[tl]);
+      a_ready_arrive(tl);
     };
 
-    if ((int64_t)blockIdx.x < n_pairs) {
+    if (first < n_pairs) {
 #pragma unroll 1
-      for (int tl = 0; tl < 2; ++tl) prologue(blockIdx.x, tl);
+      for (int tl = 0; tl < 2; ++tl) prologue(first, tl);
     }
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = first; pair < n_pairs; pair += stride) {
       for (int b = 0; b < BwdProg::kSteps; ++b) {
         const int zi = 8 - b;                                  // index of the dZ this step produces (b >= 1)
 #pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
-          const int64_t tile = pair * 2 + tl;
+          const int64_t tile = tile_of(pair, tl);
           const bool active = tile < n_tiles;
           uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
           const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
@@ -143,19 +174,19 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
               if (active) *reinterpret_cast<uint4*>(out + off) = pk;
             }
           }
-          tc_fence_before();
-          fence_async_smem();
-          if (b + 1 < BwdProg::kSteps) mbar_arrive(&sm.a_ready[tl]);
-          if (b + 1 == BwdProg::kSteps) {
+          if (b + 1 < BwdProg::kSteps) {
+            a_ready_arrive(tl);
+          } else {
+            tc_fence_before();
             // (bias gradients = column sums of the dZ tiles are taken by tc_wgrad_kernel, which has them in smem)
-            const int64_t next = pair + gridDim.x;
+            const int64_t next = pair + stride;
             if (next < n_pairs) prologue(next, tl);
           }
         }
       }
     }
   }
-  chain_teardown(tmem, warp);
+  if constexpr (TWO) chain2_teardown(tmem, warp); else chain_teardown(tmem, warp);
 }
 
 // =============================================================================================================
@@ -447,11 +478,31 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   const TcParams P = tc_make_params(m);
 
   if (g_bwd_parts & 1) {
-    const int64_t n_pairs = cdiv(n_tiles, 2);
-    const int grid = (int)std::min<int64_t>(n_pairs, kNumSMs);
-    const size_t smem = sizeof(ChainSmem);
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_mlp_dgrad_kernel<<<grid, kThreads, smem, st>>>((const uint8_t*)packed, (const float4*)d_pre, M, rec, dz, grads, P);
+    const bool two = tc_use_pairs() && n_tiles >= 4;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    const uint8_t* pk = (const uint8_t*)packed;
+    const float4* dp = (const float4*)d_pre;
+    const uint8_t* rec_c = rec;
+    if (two) {
+      cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(cdiv(n_tiles, 4), kNumSMs / 2)));
+      cfg.dynamicSmemBytes = sizeof(Chain2Smem);
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)cfg.dynamicSmemBytes));
+      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<true>, pk, dp, M, rec_c, dz, grads, P));
+    } else {
+      cfg.gridDim = dim3((unsigned)std::min<int64_t>(cdiv(n_tiles, 2), kNumSMs));
+      cfg.dynamicSmemBytes = sizeof(ChainSmem);
+      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)cfg.dynamicSmemBytes));
+      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<false>, pk, dp, M, rec_c, dz, grads, P));
+    }
     KN_LAUNCH_CHECK();
   }
   if (g_bwd_parts & 2) {

@@ -64,14 +64,51 @@ struct BwdProg {
 };
 constexpr int kBwdBlobBytes = BwdProg::blob_off(BwdProg::kSteps);
 
+// ---- cta_group::2 ("pair") weight layout ---------------------------------------------------------------------
+// The chain kernels run as CTA pairs (cluster of 2): one M = 256 tcgen05.mma per K = 16 covers a 128-sample tile
+// in EACH CTA, and each CTA holds only HALF of the weight rows (N/2), so per SM the L2 -> smem weight traffic and
+// the B-operand smem reads are halved.  Stages are K = 64 wide (four MMAs per full/empty barrier round, which
+// keeps the single issuing thread ahead of the tensor pipe) and every (stage, CTA) piece is contiguous in the
+// blob, so a stage is ONE bulk copy per CTA:
+//   step s: [stage 0: cta0 piece | cta1 piece][stage 1: ...] ... [bias stage: cta0 | cta1]
+//   piece = [k/8 chunks][N/2 rows][8]   (k = 64, or the 32-wide tail of the direction encoding, or 16 for the bias)
+constexpr int kPairK = 64;
+constexpr int kNumStages2 = 4;
+constexpr int kStageBytes2 = 128 * kPairK * 2;     // 16 KB ring slot (N/2 <= 128 rows)
+template <class Prog>
+struct PairLayout {
+  __host__ __device__ static constexpr int ktot(int s) { return (Prog::nk_h(s) + Prog::nk_x(s)) * kKStage; }
+  __host__ __device__ static constexpr int kh(int s) { return Prog::nk_h(s) * kKStage; }      // K fed by hs, rest by xs
+  __host__ __device__ static constexpr int n_data(int s) { return (ktot(s) + kPairK - 1) / kPairK; }
+  __host__ __device__ static constexpr int n_stages(int s) { return n_data(s) + (Prog::kHasBias ? 1 : 0); }
+  __host__ __device__ static constexpr int stage_k(int s, int i) {
+    return i < n_data(s) ? (ktot(s) - i * kPairK < kPairK ? ktot(s) - i * kPairK : kPairK) : 16;
+  }
+  // bytes of ONE CTA's piece: (k/8 chunks) x (N/2 rows) x 16 B
+  __host__ __device__ static constexpr int piece_bytes(int s, int i) { return stage_k(s, i) * Prog::N(s); }
+  __host__ __device__ static constexpr int step_bytes(int s) {
+    return 2 * Prog::N(s) * (ktot(s) + (Prog::kHasBias ? 16 : 0));
+  }
+  __host__ __device__ static constexpr int blob_off(int s) {
+    int off = 0;
+    for (int i = 0; i < s; ++i) off += step_bytes(i);
+    return off;
+  }
+  // offset of stage i of step s (CTA 0's piece; CTA 1's follows at + piece_bytes) relative to blob_off(s)
+  __host__ __device__ static constexpr int stage_off(int s, int i) { return 2 * Prog::N(s) * (i < n_data(s) ? i * kPairK : ktot(s)); }
+  static constexpr int kBytes = blob_off(Prog::kSteps);
+};
+
 // ---- packed weight buffer ------------------------------------------------------------------------------------
-// [forward blob][dgrad blob][fp32 side table].  The side table holds 16-byte aligned copies (the Keras flat
-// buffer is not aligned: the 1-wide sigma bias shifts everything after it): bias[l] at l*256 (l = 0..11),
-// sigma kernel [256] at 12*256, rgb kernel [128,3] at 13*256.
+// [forward blob][dgrad blob][fp32 side table][forward pair blob][dgrad pair blob].  The side table holds 16-byte
+// aligned copies (the Keras flat buffer is not aligned: the 1-wide sigma bias shifts everything after it):
+// bias[l] at l*256 (l = 0..11), sigma kernel [256] at 12*256, rgb kernel [128,3] at 13*256.
 constexpr int kBwdBlobOff = kFwdBlobBytes;
 constexpr int kAuxOff = kBwdBlobOff + kBwdBlobBytes;
 constexpr int kAuxFloats = 12 * 256 + 256 + 512;
-constexpr int kPackedBytes = kAuxOff + kAuxFloats * 4;
+constexpr int kFwdPairOff = kAuxOff + kAuxFloats * 4;
+constexpr int kBwdPairOff = kFwdPairOff + PairLayout<FwdProg>::kBytes;
+constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
 
 struct TcParams {
   int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
@@ -91,6 +128,15 @@ constexpr int kDzF = 8 * kHSBytes;                 // d features   64 KB
 constexpr int kDzG = kDzF + kHSBytes;              // d rgb_features 32 KB
 constexpr int kDzP = kDzG + 32768;                 // (d rgb_pre[3], d sigma_pre, 0...) [2 chunks][128][8]  4 KB
 constexpr int kDzBytes = kDzP + 4096;              // 612 KB per 128 samples
+
+struct Chain2Smem {
+  uint8_t hs[2][kHSBytes];
+  uint8_t xs[2][kXSBytes];
+  uint8_t stage[kNumStages2][kStageBytes2];
+  float part[kTileM][4];
+  uint64_t full[kNumStages2], empty[kNumStages2], a_ready[2], acc_ready[2];
+  uint32_t tmem_base;
+};
 
 struct ChainSmem {
   uint8_t hs[2][kHSBytes];

@@ -10,6 +10,24 @@ namespace knerf {
 namespace tcl {
 using namespace tc;
 
+// ---- optional in-kernel timing (build with -DKNERF_TC_TIMING; off by default, zero cost) ----------------------
+// per CTA, clock64() cycles: slot 0 producer waits for a free stage | 1 MMA thread waits for the A operand |
+// 2 MMA thread waits for a weight stage | 3 MMA thread total | 4 compute warp 2 waits for an accumulator |
+// 5 compute total | 6.. per-step epilogue cycles of compute warp 2 (16 + s for tile slot 1)
+#ifdef KNERF_TC_TIMING
+static __device__ unsigned long long g_tc_prof[160][40];
+// counters live in the thread's local memory (L1) and are flushed once at the end of the role
+#define KN_PROF_DECL() unsigned long long kn_prof[40]; for (int kn_i = 0; kn_i < 40; ++kn_i) kn_prof[kn_i] = 0ull
+#define KN_PROF_BEGIN(var) const long long var = clock64()
+#define KN_PROF_END(var, slot) kn_prof[slot] += (unsigned long long)(clock64() - var)
+#define KN_PROF_FLUSH() for (int kn_i = 0; kn_i < 40; ++kn_i) if (kn_prof[kn_i]) g_tc_prof[blockIdx.x][kn_i] += kn_prof[kn_i]
+#else
+#define KN_PROF_DECL()
+#define KN_PROF_BEGIN(var)
+#define KN_PROF_END(var, slot)
+#define KN_PROF_FLUSH()
+#endif
+
 __device__ __forceinline__ uint32_t chain_setup(ChainSmem& sm, int tid, int warp) {
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
@@ -33,6 +51,7 @@ __device__ __forceinline__ void chain_teardown(uint32_t tmem, int warp) {
 template <class Prog>
 __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __restrict__ blob, int64_t n_pairs) {
   uint32_t it = 0;
+  KN_PROF_DECL();
   for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     for (int s = 0; s < Prog::kSteps; ++s) {
       const int nk = Prog::nk_h(s) + Prog::nk_x(s);
@@ -41,7 +60,9 @@ __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __re
       for (int tl = 0; tl < 2; ++tl) {
         for (int ks = 0; ks < nk; ++ks, ++it) {
           const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1;
+          KN_PROF_BEGIN(t0);
           mbar_wait(&sm.empty[slot], ph ^ 1);
+          KN_PROF_END(t0, 0);
           mbar_arrive_expect_tx(&sm.full[slot], sb);
           tma_load_1d(sm.stage[slot], src + (size_t)ks * sb, sb, &sm.full[slot]);
         }
@@ -55,12 +76,15 @@ __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __re
       }
     }
   }
+  KN_PROF_FLUSH();
 }
 
 // warp 1, one lane: D[tile] = A[tile] * W_step^T, K = 32 per stage = two K=16 tcgen05.mma
 template <class Prog>
 __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n_pairs) {
   uint32_t it = 0, a_par[2] = {0, 0};
+  KN_PROF_DECL();
+  KN_PROF_BEGIN(t_all);
   for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     for (int s = 0; s < Prog::kSteps; ++s) {
       const int nkh = Prog::nk_h(s), nk = nkh + Prog::nk_x(s);
@@ -68,13 +92,17 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
       const uint32_t idesc = umma_idesc_bf16(kTileM, N, 0, 0);
       const uint32_t chunk_b = (uint32_t)N * 16;
       for (int tl = 0; tl < 2; ++tl) {
+        KN_PROF_BEGIN(t_a);
         mbar_wait(&sm.a_ready[tl], a_par[tl]);
+        KN_PROF_END(t_a, 1);
         a_par[tl] ^= 1;
         tc_fence_after();
         const uint32_t d_tmem = tmem + tl * 256;
         for (int ks = 0; ks < nk; ++ks, ++it) {
           const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1;
+          KN_PROF_BEGIN(t_f);
           mbar_wait(&sm.full[slot], ph);
+          KN_PROF_END(t_f, 2);
           tc_fence_after();
           const uint32_t a_base = (ks < nkh) ? smem_u32(sm.hs[tl]) + ks * 4 * kChunkA
                                              : smem_u32(sm.xs[tl]) + (ks - nkh) * 4 * kChunkA;
@@ -101,6 +129,8 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
       }
     }
   }
+  KN_PROF_END(t_all, 3);
+  KN_PROF_FLUSH();
 }
 
 // column sums of a [128 x ncols] bf16 operand sitting in shared memory (chunk-major) -> atomically added to

@@ -2,37 +2,30 @@
 // four 128-sample tiles -- two per CTA, ping-pong as before -- and every GEMM step is ONE M=256 tcgen05.mma per
 // K=16 issued by the leader CTA: each CTA feeds its own A tile and HALF of the weight rows (N/2), so the
 // shared-memory traffic per SM (operand reads + TMA writes) and the L2->SM weight traffic are both halved, which
-// is what bounds the single-CTA kernel.
+// is what bounds the single-CTA kernel.  Weight stages are K = 64 wide (tc_layout.cuh PairLayout):
+// the issuing thread spends ~150 cycles per stage on barriers, so four MMAs (512 tensor cycles) per stage keep it
+// ahead of the pipe where two (256 cycles) did not (benchmarks/micro/umma_rate.cu).
 //
-//   warp 0 lane 0 (both CTAs)  TMA producer: this CTA's half of every weight stage, 8-slot ring of 8 KB
-//   warp 1 lane 0 (peer CTA)   relay: local "stage landed" -> arrive on the leader's peer_full barrier
+//   warp 0 lane 0 (both CTAs)  TMA producer: this CTA's piece of every weight stage, ONE bulk copy, 4-slot ring
+//   warp 1 lane 0 (peer CTA)   relay: local "stage landed" -> arrive on the leader's full barrier of that slot
 //   warp 1 lane 0 (leader)     MMA issuer; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs
 //   warps 2-9    (both CTAs)   compute warps; "A operand ready" = one arrive per warp on the LEADER's barrier
 #pragma once
 
 #include "tc_layout.cuh"
 #include "tc_ptx.cuh"
+#include "tc_roles.cuh"
 
 namespace knerf {
 namespace tcl {
 using namespace tc;
 
-constexpr int kNumStages2 = 8;
-constexpr int kStageBytes2 = kStageBytes / 2;   // 8 KB: [4 chunks][128 rows][8]
-
-struct Chain2Smem {
-  uint8_t hs[2][kHSBytes];
-  uint8_t xs[2][kXSBytes];
-  uint8_t stage[kNumStages2][kStageBytes2];
-  float part[kTileM][4];
-  uint64_t full[kNumStages2], peer_full[kNumStages2], empty[kNumStages2], a_ready[2], acc_ready[2];
-  uint32_t tmem_base;
-};
-
-__device__ __forceinline__ uint32_t chain2_setup(Chain2Smem& sm, int tid, int warp) {
+__device__ __forceinline__ uint32_t chain2_setup(Chain2Smem& sm, int tid, int warp, uint32_t cta) {
   if (tid == 0) {
     for (int i = 0; i < kNumStages2; ++i) {
-      mbar_init(&sm.full[i], 1); mbar_init(&sm.peer_full[i], 1); mbar_init(&sm.empty[i], 1);
+      // leader: its own producer (arrive + tx bytes) and the peer's relay; peer: its producer only
+      mbar_init(&sm.full[i], cta == 0 ? 2 : 1);
+      mbar_init(&sm.empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.a_ready[i], 16); mbar_init(&sm.acc_ready[i], 1); }
     fence_mbar_init();
@@ -50,51 +43,50 @@ __device__ __forceinline__ void chain2_teardown(uint32_t tmem, int warp) {
   if (warp == 1) tmem_dealloc_2cta<512>(tmem);
 }
 
-// the 1-CTA blob layout [chunks][N][8] is reused: this CTA's half of a stage = `chunks` pieces of N/2 rows
+// `blob` = the pair blob of this program (PairLayout<Prog>)
 template <class Prog>
 __device__ __forceinline__ void producer2_role(Chain2Smem& sm, const uint8_t* __restrict__ blob, uint32_t cta,
                                                int64_t n_quads, int64_t first, int64_t stride) {
+  using PL = PairLayout<Prog>;
   uint32_t it = 0;
+  KN_PROF_DECL();
   for (int64_t quad = first; quad < n_quads; quad += stride) {
+#pragma unroll 1
     for (int s = 0; s < Prog::kSteps; ++s) {
-      const int nk = Prog::nk_h(s) + Prog::nk_x(s);
-      const uint32_t sb = Prog::stage_bytes(s);            // full-N stage bytes in the blob
-      const uint32_t piece = Prog::N(s) * 8;               // N/2 rows x 16 B
-      const uint8_t* src = blob + Prog::blob_off(s) + cta * piece;
+      const int ns = PL::n_stages(s);
+      const uint8_t* step_src = blob + PL::blob_off(s);
+#pragma unroll 1
       for (int tl = 0; tl < 2; ++tl) {
-        for (int ks = 0; ks < nk; ++ks, ++it) {
+#pragma unroll 1
+        for (int i = 0; i < ns; ++i, ++it) {
           const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
+          const uint32_t pb = PL::piece_bytes(s, i);
+          KN_PROF_BEGIN(t0);
           mbar_wait_cluster(&sm.empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&sm.full[slot], 4 * piece);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tma_load_1d(sm.stage[slot] + c * piece, src + (size_t)ks * sb + c * 2 * piece, piece, &sm.full[slot]);
-        }
-        if (Prog::kHasBias) {
-          const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
-          mbar_wait_cluster(&sm.empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&sm.full[slot], 2 * piece);
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-            tma_load_1d(sm.stage[slot] + c * piece, src + (size_t)nk * sb + c * 2 * piece, piece, &sm.full[slot]);
-          ++it;
+          KN_PROF_END(t0, 0);
+          mbar_arrive_expect_tx(&sm.full[slot], pb);
+          tma_load_1d(sm.stage[slot], step_src + PL::stage_off(s, i) + cta * pb, pb, &sm.full[slot]);
         }
       }
     }
   }
+  KN_PROF_FLUSH();
 }
 
-// peer CTA: forward "my half of slot k has landed" to the leader, in ring order
+// peer CTA: forward "my piece of slot k has landed" to the leader's full barrier, in ring order
 template <class Prog>
 __device__ __forceinline__ void relay_role(Chain2Smem& sm, int64_t n_quads, int64_t first, int64_t stride) {
+  using PL = PairLayout<Prog>;
   uint32_t it = 0;
   for (int64_t quad = first; quad < n_quads; quad += stride) {
+#pragma unroll 1
     for (int s = 0; s < Prog::kSteps; ++s) {
-      const int n = (Prog::nk_h(s) + Prog::nk_x(s) + (Prog::kHasBias ? 1 : 0)) * 2;
+      const int n = PL::n_stages(s) * 2;
+#pragma unroll 1
       for (int i = 0; i < n; ++i, ++it) {
         const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
         mbar_wait(&sm.full[slot], ph);
-        mbar_arrive_cluster(&sm.peer_full[slot], 0);
+        mbar_arrive_cluster(&sm.full[slot], 0);
       }
     }
   }
@@ -102,41 +94,59 @@ __device__ __forceinline__ void relay_role(Chain2Smem& sm, int64_t n_quads, int6
 
 template <class Prog>
 __device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, int64_t n_quads, int64_t first, int64_t stride) {
-  uint32_t it = 0, a_par[2] = {0, 0};
+  using PL = PairLayout<Prog>;
+  uint32_t it = 0, a_par = 0;   // bit tl of a_par = parity of a_ready[tl]
+  // descriptor templates: K-major SWIZZLE_NONE, SBO = 128 B, LBO = rows * 16 B; only the 14-bit start address varies
+  const uint32_t stage0 = smem_u32(sm.stage[0]);
+  KN_PROF_DECL();
+  KN_PROF_BEGIN(t_all);
   for (int64_t quad = first; quad < n_quads; quad += stride) {
+#pragma unroll 1
     for (int s = 0; s < Prog::kSteps; ++s) {
-      const int nkh = Prog::nk_h(s), nk = nkh + Prog::nk_x(s);
+      const int nd = PL::n_data(s), kh = PL::kh(s);
       const int N = Prog::N(s);
       const uint32_t idesc = umma_idesc_bf16(2 * kTileM, N, 0, 0);
       const uint32_t chunk_b = (uint32_t)N * 8;            // N/2 rows x 16 B
+      const uint64_t db0 = umma_smem_desc(stage0, chunk_b, 128);
+      const uint32_t db_step = (2 * chunk_b) >> 4;          // K = 16 further along a stage
+#pragma unroll 1
       for (int tl = 0; tl < 2; ++tl) {
-        mbar_wait_cluster(&sm.a_ready[tl], a_par[tl]);
-        a_par[tl] ^= 1;
+        const uint64_t da_hs = umma_smem_desc(smem_u32(sm.hs[tl]), kChunkA, 128);
+        const uint64_t da_xs = umma_smem_desc(smem_u32(sm.xs[tl]), kChunkA, 128);
+        KN_PROF_BEGIN(t_a);
+        mbar_wait_cluster(&sm.a_ready[tl], (a_par >> tl) & 1);
+        KN_PROF_END(t_a, 1);
+        a_par ^= 1u << tl;
         tc_fence_after();
         const uint32_t d_tmem = tmem + tl * 256;
-        for (int ks = 0; ks < nk; ++ks, ++it) {
+#pragma unroll 1
+        for (int i = 0; i < nd; ++i, ++it) {
           const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
-          mbar_wait(&sm.full[slot], ph);
-          mbar_wait_cluster(&sm.peer_full[slot], ph);
+          KN_PROF_BEGIN(t_f);
+          mbar_wait_cluster(&sm.full[slot], ph);
+          KN_PROF_END(t_f, 2);
           tc_fence_after();
-          const uint32_t a_base = (ks < nkh) ? smem_u32(sm.hs[tl]) + ks * 4 * kChunkA
-                                             : smem_u32(sm.xs[tl]) + (ks - nkh) * 4 * kChunkA;
-          const uint32_t b_base = smem_u32(sm.stage[slot]);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t da = umma_smem_desc(a_base + j * 2 * kChunkA, kChunkA, 128);
-            const uint64_t db = umma_smem_desc(b_base + j * 2 * chunk_b, chunk_b, 128);
-            umma_bf16_2cta(d_tmem, da, db, idesc, (ks > 0 || j > 0) ? 1u : 0u);
+          const int k0 = i * kPairK;
+          const uint64_t da = (k0 < kh) ? da_hs + (uint64_t)((k0 >> 3) * (kChunkA >> 4))
+                                        : da_xs + (uint64_t)(((k0 - kh) >> 3) * (kChunkA >> 4));
+          const uint64_t db = db0 + (uint64_t)(slot * (kStageBytes2 >> 4));
+          const int nm = PL::stage_k(s, i) >> 4;            // 4, or 2 for the 32-wide tail
+          umma_bf16_2cta(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);
+          umma_bf16_2cta(d_tmem, da + 2 * (kChunkA >> 4), db + db_step, idesc, 1u);
+          if (nm == 4) {
+            umma_bf16_2cta(d_tmem, da + 4 * (kChunkA >> 4), db + 2 * db_step, idesc, 1u);
+            umma_bf16_2cta(d_tmem, da + 6 * (kChunkA >> 4), db + 3 * db_step, idesc, 1u);
           }
           umma_commit_2cta(&sm.empty[slot], 3);
         }
-        if (Prog::kHasBias) {
+        if (Prog::kHasBias) {   // + 1 * bias: A = the two encoding chunks holding the constant-1 column
           const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
-          mbar_wait(&sm.full[slot], ph);
-          mbar_wait_cluster(&sm.peer_full[slot], ph);
+          KN_PROF_BEGIN(t_f);
+          mbar_wait_cluster(&sm.full[slot], ph);
+          KN_PROF_END(t_f, 2);
           tc_fence_after();
-          const uint64_t da = umma_smem_desc(smem_u32(sm.xs[tl]) + Prog::bias_a_chunk(s) * kChunkA, kChunkA, 128);
-          const uint64_t db = umma_smem_desc(smem_u32(sm.stage[slot]), chunk_b, 128);
+          const uint64_t da = da_xs + (uint64_t)(Prog::bias_a_chunk(s) * (kChunkA >> 4));
+          const uint64_t db = db0 + (uint64_t)(slot * (kStageBytes2 >> 4));
           umma_bf16_2cta(d_tmem, da, db, idesc, 1u);
           umma_commit_2cta(&sm.empty[slot], 3);
           ++it;
@@ -145,6 +155,8 @@ __device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, int64_t
       }
     }
   }
+  KN_PROF_END(t_all, 3);
+  KN_PROF_FLUSH();
 }
 
 // compute warps: "this warp's part of tile slot tl is written": publish to the async proxy, then ONE arrive per
