@@ -351,6 +351,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
               }
               tmem_ld32_wait(v);
+              uint32_t mbits = 0u;   // ReLU' bits of these 32 columns (training): what the dgrad kernel reads
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
@@ -359,6 +360,12 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 if (s < 8) {                                             // mlp.py:33-34
                   pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
                                   pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
+                  if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
+                    mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
+                    mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
+                    mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
+                    mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
+                  }
                 } else {                                                 // features is linear (mlp.py:42)
                   pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                   pack_bf16x2(x[6], x[7]));
@@ -373,6 +380,8 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;        // next layer's A operand, in place
                 if (save) *reinterpret_cast<uint4*>(rec_out + off) = pk;
               }
+              if (save && s < 8)
+                *reinterpret_cast<uint32_t*>(rec_t + kRecMask + s * kMaskLayerBytes + (h * 4 + gI) * 512 + r * 4) = mbits;
             }
             if (s == 7) {
               if (h == 1) sm.part[r][0] = sigdot;

@@ -130,15 +130,14 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           const int64_t tile = tile_of(pair, tl);
           const bool active = tile < n_tiles;
           uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
-          const uint8_t* mask = rec + tile * kRecBytes + kRecH0 + (b == 0 ? 0 : zi) * kHSBytes;
+          const uint8_t* mask = rec + tile * kRecBytes + kRecMask + zi * kMaskLayerBytes;
           const float dsig = tl == 0 ? dsig_keep0 : dsig_keep1;
-          // the ReLU masks do not depend on the accumulator: fetch all 16 vectors of this thread's 128 columns
-          // from HBM BEFORE waiting for the MMA so that their latency overlaps it (was the top stall: long_sb)
-          uint4 hm[16];
+          // the ReLU' bits (written by the forward, 1 bit per activation) do not depend on the accumulator: fetch
+          // this thread's 4 x 32 columns BEFORE waiting for the MMA so that the latency overlaps it
+          uint32_t mb[4] = {0u, 0u, 0u, 0u};
+          if (b >= 1 && active) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            hm[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (b >= 1 && active) hm[i] = __ldg(reinterpret_cast<const uint4*>(mask + (h * 16 + i) * kChunkA + r * 16));
+            for (int i = 0; i < 4; ++i) mb[i] = __ldg(reinterpret_cast<const uint32_t*>(mask + (h * 4 + i) * 512 + r * 4));
           }
           mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
@@ -163,10 +162,12 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
               }
               uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                     pack_bf16x2(x[6], x[7]));
-              if (b >= 1) {   // ReLU': keep where the saved forward activation is > 0 (HSET2.BF16 mask + AND)
-                const uint4 m4 = hm[gI * 4 + c8];
-                pk.x &= bf16x2_gt0_mask(m4.x); pk.y &= bf16x2_gt0_mask(m4.y);
-                pk.z &= bf16x2_gt0_mask(m4.z); pk.w &= bf16x2_gt0_mask(m4.w);
+              if (b >= 1) {   // ReLU': keep where the forward activation was > 0 (bit k -> low half, 16+k -> high half)
+                const uint32_t bits = mb[gI] >> (c8 * 4);
+                pk.x &= (bits & 0x00010001u) * 0xffffu;
+                pk.y &= ((bits >> 1) & 0x00010001u) * 0xffffu;
+                pk.z &= ((bits >> 2) & 0x00010001u) * 0xffffu;
+                pk.w &= ((bits >> 3) & 0x00010001u) * 0xffffu;
               }
               // dZ0 (last step) feeds no further GEMM: it must NOT touch hs[tl], which the other half-row thread
               // of this row may already be rebuilding for the next tile (prologue below)

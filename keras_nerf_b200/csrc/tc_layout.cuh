@@ -121,7 +121,10 @@ constexpr int kRecDS = 16384;                      // PE(dir)      [8 chunks][12
 constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
 constexpr int kRecF = kRecH0 + 8 * kHSBytes;       // features     64 KB
 constexpr int kRecG = kRecF + kHSBytes;            // rgb_features [16 chunks][128][8]  32 KB
-constexpr int kRecBytes = kRecG + 32768;           // 640 KB per 128 samples
+constexpr int kRecMask = kRecG + 32768;            // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
+constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns h*128 + g*32 + (0..31) of row r;
+                                                   //   bit i = column 2i, bit 16+i = column 2i+1 (bf16x2 packing order)
+constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 672 KB per 128 samples
 // pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
 constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB
 constexpr int kDzF = 8 * kHSBytes;                 // d features   64 KB
