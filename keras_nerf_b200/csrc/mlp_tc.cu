@@ -148,9 +148,20 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
 // writes them as four 16-byte vectors (512 contiguous bytes per warp and chunk: conflict-free), to the smem
 // operand and -- when training -- to the tile's record in HBM.
 //
-// sin/cos(2^f x): ONE accurate sincosf per coordinate at the half's base frequency (|arg| <= ~100: fast path),
+// sin/cos(2^f x): ONE sin/cos pair per coordinate at the half's base frequency (|arg| <= ~100, fast_sincos),
 // then angle doubling  sin 2a = 2 sin a cos a,  cos 2a = 1 - 2 sin^2 a.  The absolute error doubles per step
 // (<= 32 x 6e-8 after five), far below the bf16 rounding of the operand (2^-9 relative).
+// sin/cos for |x| <= a few hundred: two-term Cody-Waite reduction to [-pi, pi] (k * 2pi_hi is exact for |k| < 2^8:
+// 2pi_hi has 16 significant bits), then the MUFU units (absolute error ~4e-7 on the reduced range).  ~8
+// instructions instead of the ~80 of the full-range sincosf.
+__device__ __forceinline__ void fast_sincos(float x, float* sn, float* cs) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.28314208984375f, x);          // 2pi_hi = 0x40C90F00
+  r = fmaf(k, -4.321663826704025e-05f, r);           // 2pi - 2pi_hi
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+
 __device__ __forceinline__ void angle_double(float (&sn)[3], float (&cs)[3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -187,7 +198,7 @@ __device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, boo
   }
   float sn[3], cs[3], v[34];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) sincosf(ldexpf(p[c], 4 * h), &sn[c], &cs[c]);
+  for (int c = 0; c < 3; ++c) fast_sincos(h ? 16.f * p[c] : p[c], &sn[c], &cs[c]);
   if (h == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = p[c];
@@ -223,7 +234,7 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, boo
   }
   float sn[3], cs[3], v[18];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) sincosf(ldexpf(x[c], 2 * h), &sn[c], &cs[c]);
+  for (int c = 0; c < 3; ++c) fast_sincos(h ? 4.f * x[c] : x[c], &sn[c], &cs[c]);
   if (h == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = x[c];
@@ -248,6 +259,58 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, boo
     for (int k = 0; k < 2; ++k)
       *reinterpret_cast<uint4*>(rec + (4 + 2 * h + k) * kChunkA + r * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
+}
+
+// ---- epilogue of a hidden step: accumulator -> bf16 A operand of the next step ---------------------------------
+// Thread (row r, half h) converts 128 of the 256 columns, 32 at a time.  The bias is already in the accumulator
+// (folded into the GEMM), ReLU is fused into the bf16 conversion.  KIND 0: ReLU layer (mlp.py:33-34); 1: ReLU
+// layer 7, which also feeds the sigma head -- returns this half-row's part of relu(h7) . W_sigma on the fp32
+// values (mlp.py:40); 2: `features`, linear (mlp.py:42).  mask_out (training, KIND < 2): the ReLU' bits of the
+// tile, 1 bit per activation (tc_layout.cuh kRecMask) for the dgrad kernel.
+template <bool TRAIN, int KIND>
+__device__ __noinline__ float epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
+                                         uint8_t* __restrict__ mask_out, const float* __restrict__ wsig) {
+  float sigdot = 0.f;
+#pragma unroll 1
+  for (int gI = 0; gI < 4; ++gI) {
+    const int col0 = h * 128 + gI * 32;
+    uint32_t v[32];
+    tmem_ld32_issue(tacc + col0, v);
+    float4 ws[8];
+    if (KIND == 1) {   // sigma kernel for these 32 columns, fetched while the TMEM load is in flight
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
+    }
+    tmem_ld32_wait(v);
+    uint32_t mbits = 0u;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
+      uint4 pk;
+      if (KIND < 2) {
+        pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]), pack_bf16x2_relu(x[4], x[5]),
+                        pack_bf16x2_relu(x[6], x[7]));
+        if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
+          mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
+          mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
+          mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
+          mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
+        }
+      } else {
+        pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+      }
+      if (KIND == 1) {
+        const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
+        sigdot += fmaxf(x[0], 0.f) * w0.x + fmaxf(x[1], 0.f) * w0.y + fmaxf(x[2], 0.f) * w0.z +
+                  fmaxf(x[3], 0.f) * w0.w + fmaxf(x[4], 0.f) * w1.x + fmaxf(x[5], 0.f) * w1.y +
+                  fmaxf(x[6], 0.f) * w1.z + fmaxf(x[7], 0.f) * w1.w;
+      }
+      // next layer's A operand, in place; when training also the saved record (stored to HBM by warp 10)
+      *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
+    }
+    if (TRAIN && KIND < 2 && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
+  }
+  return sigdot;
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
@@ -283,6 +346,18 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     } else {
       if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
     }
+  } else if (warp == 10) {
+    // ============== record store (training): operand tiles h0..h7, features -> HBM, one bulk copy each ========
+    if constexpr (TRAIN) {
+      if (lane == 0) {
+        auto tile_of = [&](int64_t unit, int tl) -> int64_t {
+          return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
+        };
+        store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
+                   [&](int item, int64_t tile) { return rec + tile * kRecBytes + (item < 8 ? kRecH0 + item * kHSBytes : kRecF); },
+                   [](int) { return (uint32_t)kHSBytes; });
+      }
+    }
   } else {
     // =========================== compute warps ==========================
     const int q = warp & 3, h = (warp - 2) >> 2;
@@ -290,25 +365,39 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
-    float sig_keep0 = 0.f, sig_keep1 = 0.f;   // sigma of this thread's row, per tile slot
+    float sig_keep0 = 0.f, sig_keep1 = 0.f;   // this thread's half of the sigma dot product, per tile slot
 
     auto tile_of = [&](int64_t unit, int tl) -> int64_t {
       return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
     };
-    auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand is in smem
+    uint32_t st_pending = 0, st_par = 0;      // training: bit tl = hs[tl] is being stored / parity of st_done[tl]
+    // this thread's (warp's) part of the next A operand is in smem; `record`: the tile is also a saved record
+    auto a_ready_arrive = [&](int tl, bool record) {
       if constexpr (TWO) {
         a_ready_arrive2(sm, tl, lane);
       } else {
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(&sm.a_ready[tl]);
+        if (TRAIN) __syncwarp();
+      }
+      if (TRAIN && record) {
+        st_ready_arrive(&sm.st_ready[tl], lane);
+        st_pending |= 1u << tl;
+      }
+    };
+    auto hs_writable = [&](int tl) {          // the bulk store of the previous contents of hs[tl] has read them
+      if (TRAIN && ((st_pending >> tl) & 1)) {
+        mbar_wait(&sm.st_done[tl], (st_par >> tl) & 1);
+        st_par ^= 1u << tl;
+        st_pending &= ~(1u << tl);
       }
     };
     auto prologue = [&](int64_t pair, int tl) {
       const int64_t tile = tile_of(pair, tl);
       const int64_t g = tile * kTileM + r;
       pe_xyz(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRecBytes + kRecXS : nullptr, r, h, g < M, o, d, t, g, S);
-      a_ready_arrive(tl);
+      a_ready_arrive(tl, false);
     };
 
     KN_PROF_DECL();
@@ -337,66 +426,24 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           if (s < 9) {
             // hidden layers (ReLU) and `features` (linear): 128 of the 256 columns per thread.  The bias is
             // already in the accumulator (folded into the GEMM), ReLU is fused into the bf16 conversion.
-            uint8_t* rec_out = rec_t + (s < 8 ? kRecH0 + s * kHSBytes : kRecF);
-            float sigdot = 0.f;
-            const float* wsig = aux + 12 * 256;
-#pragma unroll 1
-            for (int gI = 0; gI < 4; ++gI) {
-              const int col0 = h * 128 + gI * 32;
-              uint32_t v[32];
-              tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
-              float4 ws[8];
-              if (s == 7) {   // sigma kernel for these 32 columns, fetched while the TMEM load is in flight
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
-              }
-              tmem_ld32_wait(v);
-              uint32_t mbits = 0u;   // ReLU' bits of these 32 columns (training): what the dgrad kernel reads
-#pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                const int col = col0 + c8 * 8;
-                const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
-                uint4 pk;
-                if (s < 8) {                                             // mlp.py:33-34
-                  pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
-                                  pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
-                  if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
-                    mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
-                    mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
-                    mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
-                    mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
-                  }
-                } else {                                                 // features is linear (mlp.py:42)
-                  pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                  pack_bf16x2(x[6], x[7]));
-                }
-                if (s == 7) {                                            // sigma head on the fp32 h7 (mlp.py:40)
-                  const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
-                  sigdot += fmaxf(x[0], 0.f) * w0.x + fmaxf(x[1], 0.f) * w0.y + fmaxf(x[2], 0.f) * w0.z +
-                            fmaxf(x[3], 0.f) * w0.w + fmaxf(x[4], 0.f) * w1.x + fmaxf(x[5], 0.f) * w1.y +
-                            fmaxf(x[6], 0.f) * w1.z + fmaxf(x[7], 0.f) * w1.w;
-                }
-                const int off = (col >> 3) * kChunkA + r * 16;
-                *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;        // next layer's A operand, in place
-                if (save) *reinterpret_cast<uint4*>(rec_out + off) = pk;
-              }
-              if (save && s < 8)
-                *reinterpret_cast<uint32_t*>(rec_t + kRecMask + s * kMaskLayerBytes + (h * 4 + gI) * 512 + r * 4) = mbits;
-            }
+            hs_writable(tl);
+            const uint32_t tacc = tmem + lane_base + tl * 256;
+            uint8_t* mask_out = (save && s < 8) ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr;
+            // three separately instantiated bodies: in one merged loop the compiler if-converts the sigma dot
+            // product and runs it on EVERY step (it doubled the epilogue time of the plain ReLU layers)
             if (s == 7) {
-              if (h == 1) sm.part[r][0] = sigdot;
-              named_bar_sync(1, kComputeThreads);
-              if (h == 0) {
-                const float sg = fmaxf(sigdot + sm.part[r][0] + __ldg(aux + 8 * 256), 0.f);
-                if (tl == 0) sig_keep0 = sg; else sig_keep1 = sg;
-              }
-              named_bar_sync(1, kComputeThreads);
+              const float sd = epi_hidden<TRAIN, 1>(tacc, sm.hs[tl], h, r, mask_out, aux + 12 * 256);
+              if (tl == 0) sig_keep0 = sd; else sig_keep1 = sd;   // the halves meet in the s == 9 epilogue
+            } else if (s == 8) {
+              epi_hidden<TRAIN, 2>(tacc, sm.hs[tl], h, r, nullptr, nullptr);
+            } else {
+              epi_hidden<TRAIN, 0>(tacc, sm.hs[tl], h, r, mask_out, nullptr);
             }
             if (s == 5) {
               // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for rgb_features
               pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, valid, d, g, S);
             }
-            a_ready_arrive(tl);
+            a_ready_arrive(tl, true);
           } else {
             // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
             const float* wrgb = aux + 13 * 256;
@@ -428,14 +475,15 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
               }
             }
-            if (h == 1) { sm.part[r][0] = pr; sm.part[r][1] = pg; sm.part[r][2] = pb; }
+            const float sig_part = tl == 0 ? sig_keep0 : sig_keep1;
+            if (h == 1) *reinterpret_cast<float4*>(sm.part[r]) = make_float4(pr, pg, pb, sig_part);
             named_bar_sync(1, kComputeThreads);
             if (h == 0 && valid) {
               const float* brgb = aux + 11 * 256;
-              const float zr = pr + sm.part[r][0] + __ldg(brgb), zg = pg + sm.part[r][1] + __ldg(brgb + 1),
-                          zb = pb + sm.part[r][2] + __ldg(brgb + 2);
-              rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)),
-                                        tl == 0 ? sig_keep0 : sig_keep1);
+              const float4 o4 = *reinterpret_cast<const float4*>(sm.part[r]);
+              const float zr = pr + o4.x + __ldg(brgb), zg = pg + o4.y + __ldg(brgb + 1), zb = pb + o4.z + __ldg(brgb + 2);
+              const float sg = fmaxf(sig_part + o4.w + __ldg(aux + 8 * 256), 0.f);          // mlp.py:40
+              rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)), sg);
             }
             named_bar_sync(1, kComputeThreads);
             tc_fence_before();

@@ -26,6 +26,50 @@ namespace {
 // =============================================================================================================
 // dgrad chain
 // =============================================================================================================
+// epilogue of one dgrad step: accumulator (dH = dZ_next W^T) -> pre-activation gradient tile, bf16.
+// KIND 0: d(features), linear, no mask;  1: dZ7 = (dH + d(sigma_pre) Ws^T) * ReLU'(h7) -- the sigma head shares h7
+// with `features`;  2: dZ_l = dH * ReLU'(h_l), l = 6..1;  3: dZ0, the last step: feeds no further GEMM, so it goes
+// to HBM directly (dst = record or nullptr) and must NOT touch hs[tl], which the other half-row thread of this
+// row may already be rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10)
+// the dZ record.  mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
+template <int KIND>
+__device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, const uint32_t (&mb)[4],
+                                       float dsig, const float* __restrict__ wsig) {
+#pragma unroll
+  for (int gI = 0; gI < 4; ++gI) {
+    const int col0 = h * 128 + gI * 32;
+    uint32_t v[32];
+    tmem_ld32_issue(tacc + col0, v);
+    float4 ws[8];
+    if (KIND == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
+    }
+    tmem_ld32_wait(v);
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[c8 * 8 + e]);
+      if (KIND == 1) {
+        const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
+        x[0] += dsig * w0.x; x[1] += dsig * w0.y; x[2] += dsig * w0.z; x[3] += dsig * w0.w;
+        x[4] += dsig * w1.x; x[5] += dsig * w1.y; x[6] += dsig * w1.z; x[7] += dsig * w1.w;
+      }
+      uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                            pack_bf16x2(x[6], x[7]));
+      if (KIND >= 1) {
+        const uint32_t bits = mb[gI] >> (c8 * 4);
+        pk.x &= (bits & 0x00010001u) * 0xffffu;
+        pk.y &= ((bits >> 1) & 0x00010001u) * 0xffffu;
+        pk.z &= ((bits >> 2) & 0x00010001u) * 0xffffu;
+        pk.w &= ((bits >> 3) & 0x00010001u) * 0xffffu;
+      }
+      if (KIND < 3 || dst != nullptr) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
+    }
+  }
+}
+
 // TWO = false: one CTA per SM works alone.  TWO = true: clusters of 2, cta_group::2 MMAs (tc_roles2.cuh); a work
 // unit is then four tiles (two per CTA).
 template <bool TWO>
@@ -57,17 +101,41 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     } else {
       if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
     }
+  } else if (warp == 10) {
+    // record store: every A operand of the chain is also a dZ record for the weight-gradient kernel -- item 0 = dG
+    // (prologue, 128 columns), item 1 = dF, items 2..8 = dZ7..dZ1; one bulk copy each (tc_roles.cuh store_role)
+    if (lane == 0) {
+      auto tile_of = [&](int64_t unit, int tl) -> int64_t {
+        return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
+      };
+      store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
+                 [&](int item, int64_t tile) {
+                   return dz + tile * kDzBytes + (item == 0 ? kDzG : item == 1 ? kDzF : kDzZ0 + (9 - item) * kHSBytes);
+                 },
+                 [](int item) { return (uint32_t)(item == 0 ? 32768 : kHSBytes); });
+    }
   } else {
     auto tile_of = [&](int64_t unit, int tl) -> int64_t {
       return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
     };
-    auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand is in smem
+    uint32_t st_pending = 0, st_par = 0;      // bit tl = hs[tl] is being stored / parity of st_done[tl]
+    auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand (= dZ record) is in smem
       if constexpr (TWO) {
         a_ready_arrive2(sm, tl, lane);
       } else {
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(&sm.a_ready[tl]);
+        __syncwarp();
+      }
+      st_ready_arrive(&sm.st_ready[tl], lane);
+      st_pending |= 1u << tl;
+    };
+    auto hs_writable = [&](int tl) {          // the bulk store of the previous contents of hs[tl] has read them
+      if ((st_pending >> tl) & 1) {
+        mbar_wait(&sm.st_done[tl], (st_par >> tl) & 1);
+        st_par ^= 1u << tl;
+        st_pending &= ~(1u << tl);
       }
     };
     const int q = warp & 3, h = (warp - 2) >> 2;
@@ -100,6 +168,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           atomicAdd(grads + P.b_off[11] + 2, s2); atomicAdd(grads + P.b_off[8], s3);
         }
       }
+      hs_writable(tl);
 #pragma unroll 2
       for (int c8 = 0; c8 < 8; ++c8) {
         const int col = h * 64 + c8 * 8;
@@ -112,8 +181,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
         const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                     pack_bf16x2(x[6], x[7]));
         const int off = (col >> 3) * kChunkA + r * 16;
-        *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
-        if (active) *reinterpret_cast<uint4*>(dz_t + kDzG + off) = pk;
+        *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;   // first A operand and the dG record (warp 10 stores it)
       }
       a_ready_arrive(tl);
     };
@@ -142,39 +210,14 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
-#pragma unroll
-          for (int gI = 0; gI < 4; ++gI) {
-            const int col0 = h * 128 + gI * 32;
-            float v[32];
-            tmem_ld32(tmem + lane_base + tl * 256 + col0, v);
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              const int col = col0 + c8 * 8;
-              const int off = (col >> 3) * kChunkA + r * 16;
-              float x[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = v[c8 * 8 + e];
-              if (b == 1) {   // + d(sigma_pre) Ws^T: the sigma head shares h7 with `features`
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsig + col));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wsig + col + 4));
-                x[0] += dsig * w0.x; x[1] += dsig * w0.y; x[2] += dsig * w0.z; x[3] += dsig * w0.w;
-                x[4] += dsig * w1.x; x[5] += dsig * w1.y; x[6] += dsig * w1.z; x[7] += dsig * w1.w;
-              }
-              uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                                    pack_bf16x2(x[6], x[7]));
-              if (b >= 1) {   // ReLU': keep where the forward activation was > 0 (bit k -> low half, 16+k -> high half)
-                const uint32_t bits = mb[gI] >> (c8 * 4);
-                pk.x &= (bits & 0x00010001u) * 0xffffu;
-                pk.y &= ((bits >> 1) & 0x00010001u) * 0xffffu;
-                pk.z &= ((bits >> 2) & 0x00010001u) * 0xffffu;
-                pk.w &= ((bits >> 3) & 0x00010001u) * 0xffffu;
-              }
-              // dZ0 (last step) feeds no further GEMM: it must NOT touch hs[tl], which the other half-row thread
-              // of this row may already be rebuilding for the next tile (prologue below)
-              if (b + 1 < BwdProg::kSteps) *reinterpret_cast<uint4*>(sm.hs[tl] + off) = pk;
-              if (active) *reinterpret_cast<uint4*>(out + off) = pk;
-            }
-          }
+          if (b + 1 < BwdProg::kSteps) hs_writable(tl);
+          // separately instantiated bodies (a merged loop gets if-converted: the d(sigma) term and its loads
+          // would run on every step)
+          const uint32_t tacc = tmem + lane_base + tl * 256;
+          if (b == 0) epi_dgrad<0>(tacc, sm.hs[tl], h, r, mb, 0.f, nullptr);
+          else if (b == 1) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mb, dsig, wsig);
+          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2>(tacc, sm.hs[tl], h, r, mb, 0.f, nullptr);
+          else epi_dgrad<3>(tacc, active ? out : nullptr, h, r, mb, 0.f, nullptr);
           if (b + 1 < BwdProg::kSteps) {
             a_ready_arrive(tl);
           } else {

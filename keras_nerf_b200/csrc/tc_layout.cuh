@@ -15,7 +15,7 @@ constexpr int kNumStages = 4;
 constexpr int kHSBytes = kTileM * kU * 2;          // 64 KB: one [128 x 256] bf16 operand, chunk-major
 constexpr int kXSBytes = kTileM * 64 * 2;          // 16 KB
 constexpr int kChunkA = kTileM * 16;               // bytes between 8-element chunks of a 128-row operand (2048)
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;                      // warps: 0 TMA producer, 1 MMA issuer / relay, 2-9 compute, 10 record store
 constexpr int kComputeThreads = 256;
 
 // ---- forward steps ---------------------------------------------------------------------------------------
@@ -137,7 +137,7 @@ struct Chain2Smem {
   uint8_t xs[2][kXSBytes];
   uint8_t stage[kNumStages2][kStageBytes2];
   float part[kTileM][4];
-  uint64_t full[kNumStages2], empty[kNumStages2], a_ready[2], acc_ready[2];
+  uint64_t full[kNumStages2], empty[kNumStages2], a_ready[2], acc_ready[2], st_ready[2], st_done[2];
   uint32_t tmem_base;
 };
 
@@ -146,7 +146,7 @@ struct ChainSmem {
   uint8_t xs[2][kXSBytes];
   uint8_t stage[kNumStages][kStageBytes];
   float part[kTileM][4];
-  uint64_t full[kNumStages], empty[kNumStages], a_ready[2], acc_ready[2];
+  uint64_t full[kNumStages], empty[kNumStages], a_ready[2], acc_ready[2], st_ready[2], st_done[2];
   uint32_t tmem_base;
 };
 

@@ -31,7 +31,10 @@ static __device__ unsigned long long g_tc_prof[160][40];
 __device__ __forceinline__ uint32_t chain_setup(ChainSmem& sm, int tid, int warp) {
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.a_ready[i], kComputeThreads); mbar_init(&sm.acc_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.a_ready[i], kComputeThreads); mbar_init(&sm.acc_ready[i], 1);
+      mbar_init(&sm.st_ready[i], 8); mbar_init(&sm.st_done[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&sm.tmem_base);
@@ -131,6 +134,40 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
   }
   KN_PROF_END(t_all, 3);
   KN_PROF_FLUSH();
+}
+
+// warp 10, one lane (training kernels): every operand tile the compute warps leave in hs[tl] is also a saved
+// record -- written to HBM by ONE bulk store instead of 16 STG.128 per compute thread.  Protocol per tile slot:
+// compute warps arrive on st_ready[tl] (one arrive per warp) once their part of hs[tl] is written and fenced;
+// this thread stores the tile, waits until the copy engine has read shared memory and arrives on st_done[tl],
+// which the compute warps wait for before they overwrite hs[tl] in their next epilogue.
+// dst(item, tile) -> destination (nullptr: nothing to store for this item), bytes(item) -> size.
+template <class Smem, class TileOf, class Dst, class Bytes>
+__device__ __forceinline__ void store_role(Smem& sm, int items_per_tile, int64_t n_tiles, int64_t n_units, int64_t first,
+                                           int64_t stride, TileOf tile_of, Dst dst, Bytes bytes) {
+  uint32_t par = 0;
+  for (int64_t unit = first; unit < n_units; unit += stride) {
+#pragma unroll 1
+    for (int item = 0; item < items_per_tile; ++item) {
+#pragma unroll 1
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t tile = tile_of(unit, tl);
+        mbar_wait(&sm.st_ready[tl], (par >> tl) & 1);
+        par ^= 1u << tl;
+        if (tile < n_tiles) {
+          tma_store_1d(dst(item, tile), sm.hs[tl], bytes(item));
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        mbar_arrive(&sm.st_done[tl]);
+      }
+    }
+  }
+}
+
+// compute warps, after their writes to hs[tl] are fenced (fence.proxy.async) and the warp has converged
+__device__ __forceinline__ void st_ready_arrive(uint64_t* bar, int lane) {
+  if (lane == 0) mbar_arrive(bar);
 }
 
 // column sums of a [128 x ncols] bf16 operand sitting in shared memory (chunk-major) -> atomically added to

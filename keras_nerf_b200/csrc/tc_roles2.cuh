@@ -27,7 +27,10 @@ __device__ __forceinline__ uint32_t chain2_setup(Chain2Smem& sm, int tid, int wa
       mbar_init(&sm.full[i], cta == 0 ? 2 : 1);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.a_ready[i], 16); mbar_init(&sm.acc_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.a_ready[i], 16); mbar_init(&sm.acc_ready[i], 1);
+      mbar_init(&sm.st_ready[i], 8); mbar_init(&sm.st_done[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta<512>(&sm.tmem_base);
