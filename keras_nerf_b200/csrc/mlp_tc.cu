@@ -187,15 +187,31 @@ __device__ __forceinline__ void store_cols(uint8_t* xs, uint8_t* rec, int r, int
 // PE_10(o + d t) -> 63 columns + the constant-1 column 63 (carries the folded bias, tc_layout.cuh).
 // Column order (utils.py:176-186): x y z, then per frequency f: sin(2^f xyz), cos(2^f xyz).
 // h = 0: columns 0..31 (identity, f = 0..3, f = 4 up to cos y);  h = 1: columns 32..63 (cos(2^4 z), f = 5..9, 1).
-__device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, bool valid, const float* __restrict__ o,
-                                    const float* __restrict__ d, const float* __restrict__ t, int64_t g, int S) {
-  float p[3] = {0.f, 0.f, 0.f};
-  if (valid) {
-    const int64_t ray = g / S;
+// ray origin, direction and depth of one sample: loaded EARLY (start of the epilogue that precedes the encoding) so
+// that the global-memory latency hides behind that epilogue
+// (no local memory anywhere in these kernels: with 227 KB of shared memory the SM has no L1 left, a spill or a
+// by-reference struct would be an L2 round trip)
+__device__ __forceinline__ void load_sample(float (&p)[3], const float* __restrict__ o, const float* __restrict__ d,
+                                            const float* __restrict__ t, int64_t g, int64_t M, int S) {
+  p[0] = p[1] = p[2] = 0.f;
+  if (g < M) {
+    const uint32_t ray = (uint32_t)g / (uint32_t)S;   // M < 2^31 (checked by the launcher)
     const float tt = __ldg(t + g);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(__ldg(o + ray * 3 + c), __fmul_rn(__ldg(d + ray * 3 + c), tt));
+    for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(__ldg(o + ray * 3 + c), __fmul_rn(__ldg(d + ray * 3 + c), tt));   // utils.py:193-196
   }
+}
+__device__ __forceinline__ void load_dir(float (&x)[3], const float* __restrict__ d, int64_t g, int64_t M, int S) {
+  x[0] = x[1] = x[2] = 0.f;
+  if (g < M) {
+    const uint32_t ray = (uint32_t)g / (uint32_t)S;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = __ldg(d + ray * 3 + c);
+  }
+}
+
+__device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, float px, float py, float pz) {
+  const float p[3] = {px, py, pz};
   float sn[3], cs[3], v[34];
 #pragma unroll
   for (int c = 0; c < 3; ++c) fast_sincos(h ? 16.f * p[c] : p[c], &sn[c], &cs[c]);
@@ -224,14 +240,8 @@ __device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, boo
 // PE_4(d) -> 27 columns, zeros in 27..30, the constant-1 column 31 (folded bias of steps 6..9) into chunks 0..3
 // of the xs buffer.  h = 0: columns 0..15 (identity, f = 0, 1, sin(4 x));  h = 1: columns 16..31.
 // The record keeps 8 chunks for this operand (one 32 KB weight-gradient unit): chunks 4..7 are written as zeros.
-__device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, bool valid, const float* __restrict__ d,
-                                    int64_t g, int S) {
-  float x[3] = {0.f, 0.f, 0.f};
-  if (valid) {
-    const int64_t ray = g / S;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) x[c] = __ldg(d + ray * 3 + c);
-  }
+__device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, float x0, float x1, float x2) {
+  const float x[3] = {x0, x1, x2};
   float sn[3], cs[3], v[18];
 #pragma unroll
   for (int c = 0; c < 3; ++c) fast_sincos(h ? 4.f * x[c] : x[c], &sn[c], &cs[c]);
@@ -261,6 +271,10 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, boo
   }
 }
 
+// fp32 head weights staged in the dead half of a tile's encoding buffer: [0,256) sigma kernel, [256,640) rgb
+// kernel [128,3], [640,644) b_sigma, b_rgb
+__device__ __forceinline__ float* head_smem(uint8_t* xs) { return reinterpret_cast<float*>(xs + 4 * kChunkA); }
+
 // ---- epilogue of a hidden step: accumulator -> bf16 A operand of the next step ---------------------------------
 // Thread (row r, half h) converts 128 of the 256 columns, 32 at a time.  The bias is already in the accumulator
 // (folded into the GEMM), ReLU is fused into the bf16 conversion.  KIND 0: ReLU layer (mlp.py:33-34); 1: ReLU
@@ -270,7 +284,7 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, boo
 template <bool TRAIN, int KIND>
 __device__ __noinline__ float epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
                                          uint8_t* __restrict__ mask_out, const float* __restrict__ wsig) {
-  float sigdot = 0.f;
+  float sig[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains: one accumulator serialises 128 dependent FFMAs
 #pragma unroll 1
   for (int gI = 0; gI < 4; ++gI) {
     const int col0 = h * 128 + gI * 32;
@@ -279,7 +293,7 @@ __device__ __noinline__ float epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs
     float4 ws[8];
     if (KIND == 1) {   // sigma kernel for these 32 columns, fetched while the TMEM load is in flight
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
+      for (int i = 0; i < 8; ++i) ws[i] = *(reinterpret_cast<const float4*>(wsig + col0) + i);   // shared memory
     }
     tmem_ld32_wait(v);
     uint32_t mbits = 0u;
@@ -301,16 +315,17 @@ __device__ __noinline__ float epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs
       }
       if (KIND == 1) {
         const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
-        sigdot += fmaxf(x[0], 0.f) * w0.x + fmaxf(x[1], 0.f) * w0.y + fmaxf(x[2], 0.f) * w0.z +
-                  fmaxf(x[3], 0.f) * w0.w + fmaxf(x[4], 0.f) * w1.x + fmaxf(x[5], 0.f) * w1.y +
-                  fmaxf(x[6], 0.f) * w1.z + fmaxf(x[7], 0.f) * w1.w;
+        sig[0] = fmaf(fmaxf(x[0], 0.f), w0.x, sig[0]); sig[1] = fmaf(fmaxf(x[1], 0.f), w0.y, sig[1]);
+        sig[2] = fmaf(fmaxf(x[2], 0.f), w0.z, sig[2]); sig[3] = fmaf(fmaxf(x[3], 0.f), w0.w, sig[3]);
+        sig[0] = fmaf(fmaxf(x[4], 0.f), w1.x, sig[0]); sig[1] = fmaf(fmaxf(x[5], 0.f), w1.y, sig[1]);
+        sig[2] = fmaf(fmaxf(x[6], 0.f), w1.z, sig[2]); sig[3] = fmaf(fmaxf(x[7], 0.f), w1.w, sig[3]);
       }
       // next layer's A operand, in place; when training also the saved record (stored to HBM by warp 10)
       *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
     }
     if (TRAIN && KIND < 2 && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
   }
-  return sigdot;
+  return (sig[0] + sig[1]) + (sig[2] + sig[3]);
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
@@ -346,14 +361,14 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     } else {
       if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
     }
-  } else if (warp == 10) {
+  } else if (warp >= 10) {
     // ============== record store (training): operand tiles h0..h7, features -> HBM, one bulk copy each ========
     if constexpr (TRAIN) {
       if (lane == 0) {
         auto tile_of = [&](int64_t unit, int tl) -> int64_t {
           return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
         };
-        store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
+        store_role(sm, warp - 10, 9, n_tiles, n_pairs, first, stride, tile_of,
                    [&](int item, int64_t tile) { return rec + tile * kRecBytes + (item < 8 ? kRecH0 + item * kHSBytes : kRecF); },
                    [](int) { return (uint32_t)kHSBytes; });
       }
@@ -363,6 +378,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int ctid = tid - 64;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
     float sig_keep0 = 0.f, sig_keep1 = 0.f;   // this thread's half of the sigma dot product, per tile slot
@@ -393,10 +409,9 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         st_pending &= ~(1u << tl);
       }
     };
-    auto prologue = [&](int64_t pair, int tl) {
+    auto prologue = [&](int64_t pair, int tl, const float (&p)[3]) {
       const int64_t tile = tile_of(pair, tl);
-      const int64_t g = tile * kTileM + r;
-      pe_xyz(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRecBytes + kRecXS : nullptr, r, h, g < M, o, d, t, g, S);
+      pe_xyz(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRecBytes + kRecXS : nullptr, r, h, p[0], p[1], p[2]);
       a_ready_arrive(tl, false);
     };
 
@@ -404,7 +419,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     KN_PROF_BEGIN(t_c);
     if (first < n_pairs) {
 #pragma unroll 1
-      for (int tl = 0; tl < 2; ++tl) prologue(first, tl);
+      for (int tl = 0; tl < 2; ++tl) {
+        float p0[3];
+        load_sample(p0, o, d, t, tile_of(first, tl) * kTileM + r, M, S);
+        prologue(first, tl, p0);
+      }
     }
     for (int64_t pair = first; pair < n_pairs; pair += stride) {
       for (int s = 0; s < FwdProg::kSteps; ++s) {
@@ -426,13 +445,22 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           if (s < 9) {
             // hidden layers (ReLU) and `features` (linear): 128 of the 256 columns per thread.  The bias is
             // already in the accumulator (folded into the GEMM), ReLU is fused into the bf16 conversion.
+            float dirv[3];
+            float4 headw = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s == 5) {   // fetched now, used after the epilogue: the L2 latency hides behind it
+              load_dir(dirv, d, g, M, S);
+              // head weights -> shared memory (see below): sigma kernel [256] + rgb kernel [128,3] are contiguous
+              if (ctid < 160) headw = __ldg(reinterpret_cast<const float4*>(aux + 12 * 256) + ctid);
+              else if (ctid == 160) headw = make_float4(__ldg(aux + 8 * 256), __ldg(aux + 11 * 256), __ldg(aux + 11 * 256 + 1),
+                                                        __ldg(aux + 11 * 256 + 2));
+            }
             hs_writable(tl);
             const uint32_t tacc = tmem + lane_base + tl * 256;
             uint8_t* mask_out = (save && s < 8) ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr;
             // three separately instantiated bodies: in one merged loop the compiler if-converts the sigma dot
             // product and runs it on EVERY step (it doubled the epilogue time of the plain ReLU layers)
             if (s == 7) {
-              const float sd = epi_hidden<TRAIN, 1>(tacc, sm.hs[tl], h, r, mask_out, aux + 12 * 256);
+              const float sd = epi_hidden<TRAIN, 1>(tacc, sm.hs[tl], h, r, mask_out, head_smem(sm.xs[tl]));
               if (tl == 0) sig_keep0 = sd; else sig_keep1 = sd;   // the halves meet in the s == 9 epilogue
             } else if (s == 8) {
               epi_hidden<TRAIN, 2>(tacc, sm.hs[tl], h, r, nullptr, nullptr);
@@ -441,12 +469,20 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             }
             if (s == 5) {
               // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for rgb_features
-              pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, valid, d, g, S);
+              pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, dirv[0], dirv[1], dirv[2]);
+              // Chunks 4..7 of xs[tl] are dead until the next tile's PE(xyz): they hold the fp32 weights of the two
+              // CUDA-core heads for steps 7 and 9.  (With 227 KB of shared memory the SM has no L1: every __ldg of
+              // these 2.5 KB was an L2 round trip -- 80 per thread and tile.)  Visibility to the other warps: every
+              // warp passes a_ready(5) -> MMA(6) -> acc_ready(6) before anyone reads them.
+              if (ctid <= 160) *(reinterpret_cast<float4*>(head_smem(sm.xs[tl])) + ctid) = headw;
             }
             a_ready_arrive(tl, true);
           } else {
             // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
-            const float* wrgb = aux + 13 * 256;
+            const int64_t next = pair + stride;
+            float nin[3] = {0.f, 0.f, 0.f};   // the next tile of this slot: fetch its sample now, encode it afterwards
+            if (next < n_pairs) load_sample(nin, o, d, t, tile_of(next, tl) * kTileM + r, M, S);
+            const float* wrgb = head_smem(sm.xs[tl]) + 256;
             float pr = 0.f, pg = 0.f, pb = 0.f;
 #pragma unroll 1
             for (int gI = 0; gI < 2; ++gI) {
@@ -456,7 +492,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               // rgb kernel rows col0..col0+31: 96 consecutive floats, 16-byte aligned; fetched under the TMEM load
               float4 wq[24];
 #pragma unroll
-              for (int i = 0; i < 24; ++i) wq[i] = __ldg(reinterpret_cast<const float4*>(wrgb + col0 * 3) + i);
+              for (int i = 0; i < 24; ++i) wq[i] = *(reinterpret_cast<const float4*>(wrgb + col0 * 3) + i);
               tmem_ld32_wait(v);
               const float* wv = reinterpret_cast<const float*>(wq);
 #pragma unroll
@@ -479,17 +515,16 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             if (h == 1) *reinterpret_cast<float4*>(sm.part[r]) = make_float4(pr, pg, pb, sig_part);
             named_bar_sync(1, kComputeThreads);
             if (h == 0 && valid) {
-              const float* brgb = aux + 11 * 256;
+              const float4 hb = *(reinterpret_cast<const float4*>(head_smem(sm.xs[tl])) + 160);   // b_sigma, b_rgb
               const float4 o4 = *reinterpret_cast<const float4*>(sm.part[r]);
-              const float zr = pr + o4.x + __ldg(brgb), zg = pg + o4.y + __ldg(brgb + 1), zb = pb + o4.z + __ldg(brgb + 2);
-              const float sg = fmaxf(sig_part + o4.w + __ldg(aux + 8 * 256), 0.f);          // mlp.py:40
+              const float zr = pr + o4.x + hb.y, zg = pg + o4.y + hb.z, zb = pb + o4.z + hb.w;
+              const float sg = fmaxf(sig_part + o4.w + hb.x, 0.f);                         // mlp.py:40
               rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)), sg);
             }
             named_bar_sync(1, kComputeThreads);
             tc_fence_before();
             // this tile is finished: start the next pair's tile in the same slot right away
-            const int64_t next = pair + stride;
-            if (next < n_pairs) prologue(next, tl);
+            if (next < n_pairs) prologue(next, tl, nin);
           }
           KN_PROF_END(t_e, 6 + tl * 16 + s);
         }
@@ -564,6 +599,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
                "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");
+  KN_CHECK_ARG(M < (int64_t(1) << 31), "tc_forward: at most 2^31 - 1 samples per call");
   const int64_t n_tiles = cdiv(M, kTileM);
   const bool two = tc_use_pairs() && n_tiles >= 4;
   cudaLaunchConfig_t cfg{};

@@ -33,8 +33,9 @@ namespace {
 // row may already be rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10)
 // the dZ record.  mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
 template <int KIND>
-__device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, const uint32_t (&mb)[4],
-                                       float dsig, const float* __restrict__ wsig) {
+__device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, uint4 mbv, float dsig,
+                                       const float* __restrict__ wsig) {
+  const uint32_t mb[4] = {mbv.x, mbv.y, mbv.z, mbv.w};   // by value: no local memory (no L1 on this SM)
 #pragma unroll
   for (int gI = 0; gI < 4; ++gI) {
     const int col0 = h * 128 + gI * 32;
@@ -43,7 +44,7 @@ __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst,
     float4 ws[8];
     if (KIND == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ws[i] = __ldg(reinterpret_cast<const float4*>(wsig + col0) + i);
+      for (int i = 0; i < 8; ++i) ws[i] = *(reinterpret_cast<const float4*>(wsig + col0) + i);   // shared memory
     }
     tmem_ld32_wait(v);
 #pragma unroll
@@ -101,14 +102,14 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     } else {
       if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
     }
-  } else if (warp == 10) {
+  } else if (warp >= 10) {
     // record store: every A operand of the chain is also a dZ record for the weight-gradient kernel -- item 0 = dG
     // (prologue, 128 columns), item 1 = dF, items 2..8 = dZ7..dZ1; one bulk copy each (tc_roles.cuh store_role)
     if (lane == 0) {
       auto tile_of = [&](int64_t unit, int tl) -> int64_t {
         return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
       };
-      store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
+      store_role(sm, warp - 10, 9, n_tiles, n_pairs, first, stride, tile_of,
                  [&](int item, int64_t tile) {
                    return dz + tile * kDzBytes + (item == 0 ? kDzG : item == 1 ? kDzF : kDzZ0 + (9 - item) * kHSBytes);
                  },
@@ -141,9 +142,16 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // The fp32 kernels of the two CUDA-core heads (sigma [256], rgb [128,3]) live in shared memory for the whole
+    // kernel -- the dgrad chain has no encoding operand, so xs[] is free.  With 227 KB of shared memory the SM has
+    // no L1 left: reading them with __ldg cost an L2 round trip each (224 per thread and tile).
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
-    const float* wsig = aux + 12 * 256;
-    const float* wrgb = aux + 13 * 256;
+    float* head = reinterpret_cast<float*>(sm.xs[0]);
+    for (int i = tid - 64; i < 160; i += kComputeThreads)
+      *(reinterpret_cast<float4*>(head) + i) = __ldg(reinterpret_cast<const float4*>(aux + 12 * 256) + i);
+    named_bar_sync(1, kComputeThreads);
+    const float* wsig = head;
+    const float* wrgb = head + 256;
     uint32_t acc_par[2] = {0, 0};
     float dsig_keep0 = 0.f, dsig_keep1 = 0.f;
 
@@ -173,11 +181,17 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       for (int c8 = 0; c8 < 8; ++c8) {
         const int col = h * 64 + c8 * 8;
         float x[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float* wr = wrgb + (col + e) * 3;
-          x[e] = dp.x * __ldg(wr) + dp.y * __ldg(wr + 1) + dp.z * __ldg(wr + 2);
-        }
+        // rgb kernel rows col..col+7: 24 consecutive floats, 16-byte aligned (shared memory, broadcast reads)
+        const float4* w4 = reinterpret_cast<const float4*>(wrgb + col * 3);
+        const float4 a0 = w4[0], a1 = w4[1], a2 = w4[2], a3 = w4[3], a4 = w4[4], a5 = w4[5];
+        x[0] = dp.x * a0.x + dp.y * a0.y + dp.z * a0.z;
+        x[1] = dp.x * a0.w + dp.y * a1.x + dp.z * a1.y;
+        x[2] = dp.x * a1.z + dp.y * a1.w + dp.z * a2.x;
+        x[3] = dp.x * a2.y + dp.y * a2.z + dp.z * a2.w;
+        x[4] = dp.x * a3.x + dp.y * a3.y + dp.z * a3.z;
+        x[5] = dp.x * a3.w + dp.y * a4.x + dp.z * a4.y;
+        x[6] = dp.x * a4.z + dp.y * a4.w + dp.z * a5.x;
+        x[7] = dp.x * a5.y + dp.y * a5.z + dp.z * a5.w;
         const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                     pack_bf16x2(x[6], x[7]));
         const int off = (col >> 3) * kChunkA + r * 16;
@@ -214,10 +228,11 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           // separately instantiated bodies (a merged loop gets if-converted: the d(sigma) term and its loads
           // would run on every step)
           const uint32_t tacc = tmem + lane_base + tl * 256;
-          if (b == 0) epi_dgrad<0>(tacc, sm.hs[tl], h, r, mb, 0.f, nullptr);
-          else if (b == 1) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mb, dsig, wsig);
-          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2>(tacc, sm.hs[tl], h, r, mb, 0.f, nullptr);
-          else epi_dgrad<3>(tacc, active ? out : nullptr, h, r, mb, 0.f, nullptr);
+          const uint4 mbv = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+          if (b == 0) epi_dgrad<0>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr);
+          else if (b == 1) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig);
+          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr);
+          else epi_dgrad<3>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr);
           if (b + 1 < BwdProg::kSteps) {
             a_ready_arrive(tl);
           } else {

@@ -15,7 +15,8 @@ constexpr int kNumStages = 4;
 constexpr int kHSBytes = kTileM * kU * 2;          // 64 KB: one [128 x 256] bf16 operand, chunk-major
 constexpr int kXSBytes = kTileM * 64 * 2;          // 16 KB
 constexpr int kChunkA = kTileM * 16;               // bytes between 8-element chunks of a 128-row operand (2048)
-constexpr int kThreads = 352;                      // warps: 0 TMA producer, 1 MMA issuer / relay, 2-9 compute, 10 record store
+constexpr int kThreads = 384;                      // warps: 0 TMA producer, 1 MMA issuer / relay, 2-9 compute,
+                                                   // 10-11 record store (one per tile slot; training kernels)
 constexpr int kComputeThreads = 256;
 
 // ---- forward steps ---------------------------------------------------------------------------------------

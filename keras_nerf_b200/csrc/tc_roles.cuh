@@ -54,6 +54,7 @@ __device__ __forceinline__ void chain_teardown(uint32_t tmem, int warp) {
 template <class Prog>
 __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __restrict__ blob, int64_t n_pairs) {
   uint32_t it = 0;
+  const uint64_t pol = l2_policy_evict_last();
   KN_PROF_DECL();
   for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     for (int s = 0; s < Prog::kSteps; ++s) {
@@ -67,13 +68,13 @@ __device__ __forceinline__ void producer_role(ChainSmem& sm, const uint8_t* __re
           mbar_wait(&sm.empty[slot], ph ^ 1);
           KN_PROF_END(t0, 0);
           mbar_arrive_expect_tx(&sm.full[slot], sb);
-          tma_load_1d(sm.stage[slot], src + (size_t)ks * sb, sb, &sm.full[slot]);
+          tma_load_1d_hint(sm.stage[slot], src + (size_t)ks * sb, sb, &sm.full[slot], pol);
         }
         if (Prog::kHasBias) {   // the bias "stage": [2 chunks][N][8]
           const uint32_t slot = it % kNumStages, ph = (it / kNumStages) & 1, bb = Prog::bias_bytes(s);
           mbar_wait(&sm.empty[slot], ph ^ 1);
           mbar_arrive_expect_tx(&sm.full[slot], bb);
-          tma_load_1d(sm.stage[slot], src + (size_t)nk * sb, bb, &sm.full[slot]);
+          tma_load_1d_hint(sm.stage[slot], src + (size_t)nk * sb, bb, &sm.full[slot], pol);
           ++it;
         }
       }
@@ -136,31 +137,38 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
   KN_PROF_FLUSH();
 }
 
-// warp 10, one lane (training kernels): every operand tile the compute warps leave in hs[tl] is also a saved
-// record -- written to HBM by ONE bulk store instead of 16 STG.128 per compute thread.  Protocol per tile slot:
-// compute warps arrive on st_ready[tl] (one arrive per warp) once their part of hs[tl] is written and fenced;
-// this thread stores the tile, waits until the copy engine has read shared memory and arrives on st_done[tl],
-// which the compute warps wait for before they overwrite hs[tl] in their next epilogue.
-// dst(item, tile) -> destination (nullptr: nothing to store for this item), bytes(item) -> size.
+// warps 10 and 11, one lane each (training kernels), one warp per tile slot tl: every operand tile the compute
+// warps leave in hs[tl] is also a saved record -- written to HBM by bulk copies instead of 16 STG.128 per compute
+// thread.  Protocol: compute warps arrive on st_ready[tl] (one arrive per warp) once their part of hs[tl] is
+// written and fenced; this thread stores the tile, waits until the copy engine has read shared memory and
+// arrives on st_done[tl], which the compute warps wait for before they overwrite hs[tl] in their next epilogue.
+// dst(item, tile) -> destination, bytes(item) -> size.
+// The tile goes out in 16 KB pieces with at most two in flight: a whole-tile copy ahead of them in the SM's copy
+// queue delays the weight stages (measured: the MMA thread then waits for stages a third of the time).
+constexpr uint32_t kStorePiece = 16384;
 template <class Smem, class TileOf, class Dst, class Bytes>
-__device__ __forceinline__ void store_role(Smem& sm, int items_per_tile, int64_t n_tiles, int64_t n_units, int64_t first,
-                                           int64_t stride, TileOf tile_of, Dst dst, Bytes bytes) {
+__device__ __forceinline__ void store_role(Smem& sm, int tl, int items_per_tile, int64_t n_tiles, int64_t n_units,
+                                           int64_t first, int64_t stride, TileOf tile_of, Dst dst, Bytes bytes) {
   uint32_t par = 0;
+  const uint64_t pol = l2_policy_evict_first();
   for (int64_t unit = first; unit < n_units; unit += stride) {
+    const int64_t tile = tile_of(unit, tl);
 #pragma unroll 1
     for (int item = 0; item < items_per_tile; ++item) {
+      mbar_wait(&sm.st_ready[tl], par);
+      par ^= 1u;
+      if (tile < n_tiles) {
+        uint8_t* g = dst(item, tile);
+        const uint32_t nb = bytes(item);
 #pragma unroll 1
-      for (int tl = 0; tl < 2; ++tl) {
-        const int64_t tile = tile_of(unit, tl);
-        mbar_wait(&sm.st_ready[tl], (par >> tl) & 1);
-        par ^= 1u << tl;
-        if (tile < n_tiles) {
-          tma_store_1d(dst(item, tile), sm.hs[tl], bytes(item));
+        for (uint32_t off = 0; off < nb; off += kStorePiece) {
+          tma_store_1d_hint(g + off, sm.hs[tl] + off, kStorePiece, pol);
           tma_store_commit();
-          tma_store_wait_read();
+          tma_store_wait_read_1();
         }
-        mbar_arrive(&sm.st_done[tl]);
+        tma_store_wait_read();
       }
+      mbar_arrive(&sm.st_done[tl]);
     }
   }
 }

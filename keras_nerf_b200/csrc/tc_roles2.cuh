@@ -52,6 +52,7 @@ __device__ __forceinline__ void producer2_role(Chain2Smem& sm, const uint8_t* __
                                                int64_t n_quads, int64_t first, int64_t stride) {
   using PL = PairLayout<Prog>;
   uint32_t it = 0;
+  const uint64_t pol = l2_policy_evict_last();
   KN_PROF_DECL();
   for (int64_t quad = first; quad < n_quads; quad += stride) {
 #pragma unroll 1
@@ -68,7 +69,7 @@ __device__ __forceinline__ void producer2_role(Chain2Smem& sm, const uint8_t* __
           mbar_wait_cluster(&sm.empty[slot], ph ^ 1);
           KN_PROF_END(t0, 0);
           mbar_arrive_expect_tx(&sm.full[slot], pb);
-          tma_load_1d(sm.stage[slot], step_src + PL::stage_off(s, i) + cta * pb, pb, &sm.full[slot]);
+          tma_load_1d_hint(sm.stage[slot], step_src + PL::stage_off(s, i) + cta * pb, pb, &sm.full[slot], pol);
         }
       }
     }
