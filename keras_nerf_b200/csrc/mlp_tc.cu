@@ -335,7 +335,7 @@ template <bool TRAIN, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o, const float* __restrict__ d,
                   const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
-                  uint8_t* __restrict__ rec) {
+                  uint8_t* __restrict__ rec, int ordered) {
   using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -356,19 +356,23 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     }
   } else if (warp == 1) {
     if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, n_pairs, first, stride);
+      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, 0u, ordered != 0, n_pairs, first, stride);
       else if (lane == 0) relay_role<FwdProg>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
     } else {
       if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
     }
-  } else if (warp >= 10) {
+  } else if (warp == 11) {
+    if constexpr (TWO) {
+      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
+    }
+  } else if (warp == 10) {
     // ============== record store (training): operand tiles h0..h7, features -> HBM, one bulk copy each ========
     if constexpr (TRAIN) {
       if (lane == 0) {
         auto tile_of = [&](int64_t unit, int tl) -> int64_t {
           return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
         };
-        store_role(sm, warp - 10, 9, n_tiles, n_pairs, first, stride, tile_of,
+        store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
                    [&](int item, int64_t tile) { return rec + tile * kRecBytes + (item < 8 ? kRecH0 + item * kHSBytes : kRecF); },
                    [](int) { return (uint32_t)kHSBytes; });
       }
@@ -549,8 +553,9 @@ bool tc_use_pairs() {
     const char* e = std::getenv("KNERF_TC_2CTA");
     g_tc_variant = (e != nullptr && e[0] == '0') ? 1 : 2;
   }
-  return g_tc_variant == 2;
+  return g_tc_variant >= 2;
 }
+bool tc_ordered_issue() { return g_tc_variant == 3; }
 
 // diagnostic (-DKNERF_TC_TIMING builds only): copy and clear the forward kernel's per-CTA cycle counters
 int tc_debug_timing(unsigned long long* host_out, int n) {
@@ -618,6 +623,9 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
     cfg.gridDim = dim3((unsigned)std::min<int64_t>(cdiv(n_tiles, 2), kNumSMs));
     cfg.dynamicSmemBytes = sizeof(ChainSmem);
   }
+  // MMA issue order of the pair kernels (tc_roles2.cuh): bit-reproducible when training, free-running at
+  // inference unless knerf_debug_tc_variant(3) asks for the ordered form
+  const int ordered = (training || tc_ordered_issue()) ? 1 : 0;
   const uint8_t* pk = (const uint8_t*)packed;
   float4* out = (float4*)rgbsigma;
   uint8_t* rec = training ? (uint8_t*)ws : nullptr;
@@ -625,7 +633,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   do {                                                                                                              \
     KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<TR, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                  (int)cfg.dynamicSmemBytes));                                                       \
-    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<TR, TW>, pk, o, d, t, M, S, out, rec));                       \
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<TR, TW>, pk, o, d, t, M, S, out, rec, ordered));                       \
   } while (0)
   if (training && two) KN_LAUNCH_FWD(true, true);
   else if (training) KN_LAUNCH_FWD(true, false);

@@ -97,19 +97,23 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     }
   } else if (warp == 1) {
     if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, n_pairs, first, stride);
+      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 0u, true, n_pairs, first, stride);
       else if (lane == 0) relay_role<BwdProg>(sm, n_pairs, first, stride);
     } else {
       if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
     }
-  } else if (warp >= 10) {
+  } else if (warp == 11) {
+    if constexpr (TWO) {
+      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 1u, true, n_pairs, first, stride);
+    }
+  } else if (warp == 10) {
     // record store: every A operand of the chain is also a dZ record for the weight-gradient kernel -- item 0 = dG
     // (prologue, 128 columns), item 1 = dF, items 2..8 = dZ7..dZ1; one bulk copy each (tc_roles.cuh store_role)
     if (lane == 0) {
       auto tile_of = [&](int64_t unit, int tl) -> int64_t {
         return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
       };
-      store_role(sm, warp - 10, 9, n_tiles, n_pairs, first, stride, tile_of,
+      store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
                  [&](int item, int64_t tile) {
                    return dz + tile * kDzBytes + (item == 0 ? kDzG : item == 1 ? kDzF : kDzZ0 + (9 - item) * kHSBytes);
                  },

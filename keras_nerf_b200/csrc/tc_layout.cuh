@@ -15,8 +15,11 @@ constexpr int kNumStages = 4;
 constexpr int kHSBytes = kTileM * kU * 2;          // 64 KB: one [128 x 256] bf16 operand, chunk-major
 constexpr int kXSBytes = kTileM * 64 * 2;          // 16 KB
 constexpr int kChunkA = kTileM * 16;               // bytes between 8-element chunks of a 128-row operand (2048)
-constexpr int kThreads = 384;                      // warps: 0 TMA producer, 1 MMA issuer / relay, 2-9 compute,
-                                                   // 10-11 record store (one per tile slot; training kernels)
+constexpr int kThreads = 384;                      // warps: 0 TMA producer, 1 MMA issuer (even ring items) / relay,
+                                                   // 2-9 compute, 10 record store (training kernels), 11 MMA issuer of
+                                                   // the odd ring items (pair kernels, leader CTA).  12 warps: a 13th
+                                                   // would cap ptxas at 128 registers and spill (no L1 here: a spill
+                                                   // is an L2 round trip)
 constexpr int kComputeThreads = 256;
 
 // ---- forward steps ---------------------------------------------------------------------------------------
@@ -140,6 +143,8 @@ struct Chain2Smem {
   float part[kTileM][4];
   uint64_t full[kNumStages2], empty[kNumStages2], a_ready[2], acc_ready[2], st_ready[2], st_done[2];
   uint32_t tmem_base;
+  uint32_t items_issued;      // ordered mode: ring items whose MMAs have been issued (the two issuers take turns)
+  uint32_t first_issued[2];   // unordered mode, per tile slot: GEMM steps whose first (accumulate = 0) MMA is issued
 };
 
 struct ChainSmem {

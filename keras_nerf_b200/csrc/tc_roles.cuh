@@ -137,38 +137,41 @@ __device__ __forceinline__ void mma_role(ChainSmem& sm, uint32_t tmem, int64_t n
   KN_PROF_FLUSH();
 }
 
-// warps 10 and 11, one lane each (training kernels), one warp per tile slot tl: every operand tile the compute
-// warps leave in hs[tl] is also a saved record -- written to HBM by bulk copies instead of 16 STG.128 per compute
-// thread.  Protocol: compute warps arrive on st_ready[tl] (one arrive per warp) once their part of hs[tl] is
-// written and fenced; this thread stores the tile, waits until the copy engine has read shared memory and
-// arrives on st_done[tl], which the compute warps wait for before they overwrite hs[tl] in their next epilogue.
+// warp 10, one lane (training kernels): every operand tile the compute warps leave in hs[tl] is also a saved
+// record -- written to HBM by bulk copies instead of 16 STG.128 per compute thread.  Protocol per tile slot:
+// compute warps arrive on st_ready[tl] (one arrive per warp) once their part of hs[tl] is written and fenced;
+// this thread stores the tile, waits until the copy engine has read shared memory and arrives on st_done[tl],
+// which the compute warps wait for before they overwrite hs[tl] in their next epilogue.
 // dst(item, tile) -> destination, bytes(item) -> size.
 // The tile goes out in 16 KB pieces with at most two in flight: a whole-tile copy ahead of them in the SM's copy
 // queue delays the weight stages (measured: the MMA thread then waits for stages a third of the time).
 constexpr uint32_t kStorePiece = 16384;
 template <class Smem, class TileOf, class Dst, class Bytes>
-__device__ __forceinline__ void store_role(Smem& sm, int tl, int items_per_tile, int64_t n_tiles, int64_t n_units,
-                                           int64_t first, int64_t stride, TileOf tile_of, Dst dst, Bytes bytes) {
+__device__ __forceinline__ void store_role(Smem& sm, int items_per_tile, int64_t n_tiles, int64_t n_units, int64_t first,
+                                           int64_t stride, TileOf tile_of, Dst dst, Bytes bytes) {
   uint32_t par = 0;
   const uint64_t pol = l2_policy_evict_first();
   for (int64_t unit = first; unit < n_units; unit += stride) {
-    const int64_t tile = tile_of(unit, tl);
 #pragma unroll 1
     for (int item = 0; item < items_per_tile; ++item) {
-      mbar_wait(&sm.st_ready[tl], par);
-      par ^= 1u;
-      if (tile < n_tiles) {
-        uint8_t* g = dst(item, tile);
-        const uint32_t nb = bytes(item);
 #pragma unroll 1
-        for (uint32_t off = 0; off < nb; off += kStorePiece) {
-          tma_store_1d_hint(g + off, sm.hs[tl] + off, kStorePiece, pol);
-          tma_store_commit();
-          tma_store_wait_read_1();
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t tile = tile_of(unit, tl);
+        mbar_wait(&sm.st_ready[tl], (par >> tl) & 1);
+        par ^= 1u << tl;
+        if (tile < n_tiles) {
+          uint8_t* g = dst(item, tile);
+          const uint32_t nb = bytes(item);
+#pragma unroll 1
+          for (uint32_t off = 0; off < nb; off += kStorePiece) {
+            tma_store_1d_hint(g + off, sm.hs[tl] + off, kStorePiece, pol);
+            tma_store_commit();
+            tma_store_wait_read_1();
+          }
+          tma_store_wait_read();
         }
-        tma_store_wait_read();
+        mbar_arrive(&sm.st_done[tl]);
       }
-      mbar_arrive(&sm.st_done[tl]);
     }
   }
 }

@@ -27,8 +27,10 @@ __device__ __forceinline__ uint32_t chain2_setup(Chain2Smem& sm, int tid, int wa
       mbar_init(&sm.full[i], cta == 0 ? 2 : 1);
       mbar_init(&sm.empty[i], 1);
     }
+    sm.items_issued = 0u;
+    sm.first_issued[0] = sm.first_issued[1] = 0u;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm.a_ready[i], 16); mbar_init(&sm.acc_ready[i], 1);
+      mbar_init(&sm.a_ready[i], 16); mbar_init(&sm.acc_ready[i], 2);   // acc_ready: one commit per MMA issuer
       mbar_init(&sm.st_ready[i], 8); mbar_init(&sm.st_done[i], 1);
     }
     fence_mbar_init();
@@ -96,10 +98,30 @@ __device__ __forceinline__ void relay_role(Chain2Smem& sm, int64_t n_quads, int6
   }
 }
 
+// TWO issuing threads (warps 1 and 11 of the leader CTA) take the ring items alternately: thread p issues the MMAs
+// of the items with index % 2 == p.  tcgen05.mma holds its issuing thread until the MMA has (nearly) completed --
+// measured: with one issuer every cycle it spends on barriers between two MMAs is a cycle the tensor pipe idles
+// (benchmarks/micro/umma_rate.cu: stage time = MMA time + overhead, additive, ~250 cycles per stage).  With two
+// issuers the pipe runs one thread's stage while the other waits for its next weight stage and commits.
+//  * ring slot = item % 4, so every slot has exactly ONE consumer thread: the parity waits stay sound;
+//  * both threads wait for a_ready[tl]; acc_ready[tl] expects one tcgen05.commit from each (a commit covers only
+//    the MMAs of the committing thread);
+//  * ordered = true (training kernels): the MMAs are ISSUED in ring order (items_issued, a counter in shared
+//    memory: a thread issues item j once the other has issued item j-1), so the fp32 accumulation order -- hence
+//    every output bit -- is the same as with a single issuer, run after run; the per-stage barrier work still
+//    happens before that hand-over, off the pipe's critical path;
+//  * ordered = false (inference): only the first MMA of a step (accumulate = 0, it overwrites the accumulator) is
+//    ordered before the other thread's items of that step (first_issued[tl], a step counter).  The two threads'
+//    later MMAs may interleave either way: sums of the same fp32 products in a different order, i.e. outputs
+//    can differ in the last bit from run to run -- 16 % more throughput (1475 vs 1275 TFLOP/s).
+// Accumulation into the same TMEM tile from two threads is safe: the pipe executes MMAs one at a time.
 template <class Prog>
-__device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, int64_t n_quads, int64_t first, int64_t stride) {
+__device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, uint32_t p, bool ordered, int64_t n_quads,
+                                          int64_t first, int64_t stride) {
   using PL = PairLayout<Prog>;
   uint32_t it = 0, a_par = 0;   // bit tl of a_par = parity of a_ready[tl]
+  uint32_t step_no = 0;   // GEMM steps before the current one; every step has >= 2 items, so both issuers take
+                          // part in every (step, slot)
   // descriptor templates: K-major SWIZZLE_NONE, SBO = 128 B, LBO = rows * 16 B; only the 14-bit start address varies
   const uint32_t stage0 = smem_u32(sm.stage[0]);
   KN_PROF_DECL();
@@ -108,6 +130,7 @@ __device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, int64_t
 #pragma unroll 1
     for (int s = 0; s < Prog::kSteps; ++s) {
       const int nd = PL::n_data(s), kh = PL::kh(s);
+      const int ns = PL::n_stages(s);
       const int N = Prog::N(s);
       const uint32_t idesc = umma_idesc_bf16(2 * kTileM, N, 0, 0);
       const uint32_t chunk_b = (uint32_t)N * 8;            // N/2 rows x 16 B
@@ -117,46 +140,50 @@ __device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, int64_t
       for (int tl = 0; tl < 2; ++tl) {
         const uint64_t da_hs = umma_smem_desc(smem_u32(sm.hs[tl]), kChunkA, 128);
         const uint64_t da_xs = umma_smem_desc(smem_u32(sm.xs[tl]), kChunkA, 128);
-        KN_PROF_BEGIN(t_a);
-        mbar_wait_cluster(&sm.a_ready[tl], (a_par >> tl) & 1);
-        KN_PROF_END(t_a, 1);
-        a_par ^= 1u << tl;
-        tc_fence_after();
         const uint32_t d_tmem = tmem + tl * 256;
+        volatile uint32_t* issued = &sm.items_issued;
+        volatile uint32_t* fi = &sm.first_issued[tl];
+        bool started = false;
 #pragma unroll 1
-        for (int i = 0; i < nd; ++i, ++it) {
-          const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
-          KN_PROF_BEGIN(t_f);
-          mbar_wait_cluster(&sm.full[slot], ph);
-          KN_PROF_END(t_f, 2);
-          tc_fence_after();
-          const int k0 = i * kPairK;
-          const uint64_t da = (k0 < kh) ? da_hs + (uint64_t)((k0 >> 3) * (kChunkA >> 4))
-                                        : da_xs + (uint64_t)(((k0 - kh) >> 3) * (kChunkA >> 4));
-          const uint64_t db = db0 + (uint64_t)(slot * (kStageBytes2 >> 4));
-          const int nm = PL::stage_k(s, i) >> 4;            // 4, or 2 for the 32-wide tail
-          umma_bf16_2cta(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);
-          umma_bf16_2cta(d_tmem, da + 2 * (kChunkA >> 4), db + db_step, idesc, 1u);
-          if (nm == 4) {
-            umma_bf16_2cta(d_tmem, da + 4 * (kChunkA >> 4), db + 2 * db_step, idesc, 1u);
-            umma_bf16_2cta(d_tmem, da + 6 * (kChunkA >> 4), db + 3 * db_step, idesc, 1u);
+        for (int i = 0; i < ns; ++i, ++it) {
+          if ((it & 1u) != p) continue;
+          if (!started) {   // this thread's first item of the step
+            started = true;
+            KN_PROF_BEGIN(t_a);
+            mbar_wait_cluster(&sm.a_ready[tl], (a_par >> tl) & 1);
+            if (!ordered && i > 0) { while (*fi <= step_no) {} }   // item 0 (accumulate = 0) is the other thread's
+            KN_PROF_END(t_a, 1);
+            tc_fence_after();
           }
-          umma_commit_2cta(&sm.empty[slot], 3);
-        }
-        if (Prog::kHasBias) {   // + 1 * bias: A = the two encoding chunks holding the constant-1 column
           const uint32_t slot = it % kNumStages2, ph = (it / kNumStages2) & 1;
           KN_PROF_BEGIN(t_f);
           mbar_wait_cluster(&sm.full[slot], ph);
           KN_PROF_END(t_f, 2);
-          tc_fence_after();
-          const uint64_t da = da_xs + (uint64_t)(Prog::bias_a_chunk(s) * (kChunkA >> 4));
           const uint64_t db = db0 + (uint64_t)(slot * (kStageBytes2 >> 4));
-          umma_bf16_2cta(d_tmem, da, db, idesc, 1u);
+          if (ordered) { while (*issued != it) {} }         // my turn: every earlier item has been issued
+          if (i < nd) {
+            const int k0 = i * kPairK;
+            const uint64_t da = (k0 < kh) ? da_hs + (uint64_t)((k0 >> 3) * (kChunkA >> 4))
+                                          : da_xs + (uint64_t)(((k0 - kh) >> 3) * (kChunkA >> 4));
+            const int nm = PL::stage_k(s, i) >> 4;          // 4, or 2 for the 32-wide tail
+            umma_bf16_2cta(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);
+            if (!ordered && i == 0) *fi = step_no + 1;
+            umma_bf16_2cta(d_tmem, da + 2 * (kChunkA >> 4), db + db_step, idesc, 1u);
+            if (nm == 4) {
+              umma_bf16_2cta(d_tmem, da + 4 * (kChunkA >> 4), db + 2 * db_step, idesc, 1u);
+              umma_bf16_2cta(d_tmem, da + 6 * (kChunkA >> 4), db + 3 * db_step, idesc, 1u);
+            }
+          } else {   // + 1 * bias: A = the two encoding chunks holding the constant-1 column
+            const uint64_t da = da_xs + (uint64_t)(Prog::bias_a_chunk(s) * (kChunkA >> 4));
+            umma_bf16_2cta(d_tmem, da, db, idesc, 1u);
+          }
+          if (ordered) *issued = it + 1;
           umma_commit_2cta(&sm.empty[slot], 3);
-          ++it;
         }
+        a_par ^= 1u << tl;
         umma_commit_2cta(&sm.acc_ready[tl], 3);
       }
+      ++step_no;
     }
   }
   KN_PROF_END(t_all, 3);
