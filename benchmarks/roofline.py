@@ -16,9 +16,9 @@ FLOP_TRAIN_PER_SAMPLE = 3_489_024          # fwd + dgrad + wgrad
 FLOP_WGRAD_PER_SAMPLE = 1_186_816          # every weight once more
 FLOP_DGRAD_PER_SAMPLE = FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE - FLOP_WGRAD_PER_SAMPLE
 # bf16 mode, algorithmic HBM bytes per sample (records of 672 KB + 612 KB per 128 samples)
-BYTES_FWD_SAVE = 672 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
+BYTES_FWD_SAVE = 664 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
 BYTES_DGRAD = 8 * 32 + 612 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes the dZ record
-BYTES_WGRAD = 1444 * 1024 / 128                         # operand units of the 12 weight-gradient tasks
+BYTES_WGRAD = 1388 * 1024 / 128                         # operand units of the 13 weight-gradient tasks
 # measured DRAM traffic per sample from `ncu --set full` (profiles/r01_bf16_ncu_full.md, 393,216-sample launches)
 NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.035415 + 1.963989) * 1e9 / 393216,
                           "tc_mlp_dgrad_kernel": (1.629502 + 1.882920) * 1e9 / 393216,

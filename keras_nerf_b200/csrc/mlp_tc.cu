@@ -239,7 +239,7 @@ __device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, flo
 
 // PE_4(d) -> 27 columns, zeros in 27..30, the constant-1 column 31 (folded bias of steps 6..9) into chunks 0..3
 // of the xs buffer.  h = 0: columns 0..15 (identity, f = 0, 1, sin(4 x));  h = 1: columns 16..31.
-// The record keeps 8 chunks for this operand (one 32 KB weight-gradient unit): chunks 4..7 are written as zeros.
+// (the record keeps only these 4 chunks: the weight-gradient kernel fetches 8 KB for this operand)
 __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, float x0, float x1, float x2) {
   const float x[3] = {x0, x1, x2};
   float sn[3], cs[3], v[18];
@@ -264,11 +264,6 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, flo
     v[15] = 1.f;
   }
   store_cols(xs, rec, r, 2 * h, v, 2);
-  if (rec) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      *reinterpret_cast<uint4*>(rec + (4 + 2 * h + k) * kChunkA + r * 16) = make_uint4(0u, 0u, 0u, 0u);
-  }
 }
 
 // fp32 head weights staged in the dead half of a tile's encoding buffer: [0,256) sigma kernel, [256,640) rgb

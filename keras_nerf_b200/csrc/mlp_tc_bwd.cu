@@ -287,7 +287,9 @@ static WTaskTable build_task_table() {
     WTask& t = T.t[n++];
     t.n_units = 3;
     const int bl = (layer == 0) ? 0 : -1;   // layer 5's dZ column sums are taken by its h-part task
-    t.u[0] = {0, kRecXS, kWUnitBytes, -1, 0}; t.u[1] = {1, b_off, kWUnitBytes, bl, 0};
+    // PE(xyz) is 64 features = 16 KB: only that much is fetched.  The MMA still reads a 128-feature unit; what the
+    // rest of the ring slot holds (stale bytes) only reaches accumulator rows >= 64, which are never flushed.
+    t.u[0] = {0, kRecXS, kXSBytes, -1, 0}; t.u[1] = {1, b_off, kWUnitBytes, bl, 0};
     t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes, bl, 128};
     t.n_groups = 2;
     t.g[0] = {0, 1, 0, 128, layer, row_base, 63, 0, 0, 0, 1};
@@ -313,7 +315,8 @@ static WTaskTable build_task_table() {
     WTask& t = T.t[n++];
     t.n_units = 4;
     t.u[0] = {1, kDzG, kWUnitBytes, 10, 0}; t.u[1] = {0, kRecF, kWUnitBytes, -1, 0};
-    t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes, -1, 0}; t.u[3] = {0, kRecDS, kWUnitBytes, -1, 0};
+    t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes, -1, 0};
+    t.u[3] = {0, kRecDS, 8192, -1, 0};   // PE(dir): 32 columns = 8 KB (27 valid rows of the accumulator)
     t.n_groups = 3;
     t.g[0] = {1, 0, 0, 128, 10, 0, 128, 0, 0, 1, 0};
     t.g[1] = {2, 0, 128, 128, 10, 128, 128, 0, 0, 1, 0};

@@ -121,7 +121,7 @@ struct TcParams {
 // ---- per-tile records in the training workspace (chunk-major bf16) -------------------------------------------
 // activations saved by the forward:
 constexpr int kRecXS = 0;                          // PE(xyz)      [8 chunks][128][8]   16 KB
-constexpr int kRecDS = 16384;                      // PE(dir)      [8 chunks][128][8]   16 KB (chunks 4..7 zero)
+constexpr int kRecDS = 16384;                      // PE(dir)      [4 chunks][128][8]    8 KB (the next 8 KB are unused)
 constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
 constexpr int kRecF = kRecH0 + 8 * kHSBytes;       // features     64 KB
 constexpr int kRecG = kRecF + kHSBytes;            // rgb_features [16 chunks][128][8]  32 KB
