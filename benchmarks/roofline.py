@@ -20,9 +20,9 @@ BYTES_FWD_SAVE = 664 * 1024 / 128                       # forward writes the act
 BYTES_DGRAD = 8 * 32 + 612 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes the dZ record
 BYTES_WGRAD = 1388 * 1024 / 128                         # operand units of the 13 weight-gradient tasks
 # measured DRAM traffic per sample from `ncu --set full` (profiles/r01_bf16_ncu_full.md, 393,216-sample launches)
-NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.035415 + 1.963989) * 1e9 / 393216,
-                          "tc_mlp_dgrad_kernel": (1.629502 + 1.882920) * 1e9 / 393216,
-                          "tc_wgrad_kernel": (4.524511 + 0.005662) * 1e9 / 393216}
+NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.002957 + 2.036844) * 1e9 / 393216,
+                          "tc_mlp_dgrad_kernel": (0.108136 + 1.866033) * 1e9 / 393216,
+                          "tc_wgrad_kernel": (4.355746 + 0.007782) * 1e9 / 393216}
 
 
 def _time_ms(fn, iters=5, warmup=2):
