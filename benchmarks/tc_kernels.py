@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from benchmarks.roofline import (FLOP_DGRAD_PER_SAMPLE, FLOP_FWD_PER_SAMPLE, FLOP_WGRAD_PER_SAMPLE,  # noqa: E402
-                                 _time_ms)
+from benchmarks.roofline import (FLOP_DGRAD_PER_SAMPLE, FLOP_FWD_INFER_EXECUTED, FLOP_FWD_PER_SAMPLE,  # noqa: E402
+                                 FLOP_WGRAD_PER_SAMPLE, _time_ms)
 
 
 def main():
@@ -55,6 +55,7 @@ def main():
         out[name] = {"ms": round(ms, 4), "tflops": round(flop * rows / ms / 1e9, 1), "ns_per_sample": round(ms * 1e6 / rows, 4)}
 
     rec("fwd_infer", _time_ms(lambda: fwd(0), iters), FLOP_FWD_PER_SAMPLE)
+    out["fwd_infer"]["tflops_executed"] = round(out["fwd_infer"]["tflops"] * FLOP_FWD_INFER_EXECUTED / FLOP_FWD_PER_SAMPLE, 1)
     rec("fwd_train", _time_ms(lambda: fwd(1), iters), FLOP_FWD_PER_SAMPLE)
     for name, mask, flop in (("dgrad", 1, FLOP_DGRAD_PER_SAMPLE), ("wgrad", 2, FLOP_WGRAD_PER_SAMPLE)):
         lib.knerf_debug_backward_parts(mask)

@@ -42,9 +42,37 @@ __device__ __forceinline__ float bwd_weight(const float* __restrict__ params, co
   return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * BwdProg::ld(b) + k];
 }
 
-template <class Prog, bool FWD>
+// last step of the folded inference program (tc_layout.cuh FwdFoldProg): B element at reduction index k (h7 part,
+// then the direction encoding) and output column n; the product W_f W_g is formed here, in fp32
+__device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P, int k, int n) {
+  const float* Wf = params + P.w_off[9];    // features      [256, 256]
+  const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
+  if (n < 128) {
+    if (k >= 256) return (k - 256 < 27) ? Wg[(int64_t)k * 128 + n] : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < 256; ++j) acc = fmaf(Wf[k * 256 + j], Wg[j * 128 + n], acc);
+    return acc;
+  }
+  return (n == 128 && k < 256) ? params[P.w_off[8] + k] : 0.f;   // sigma kernel [256, 1]
+}
+__device__ __forceinline__ float fold_bias(const float* __restrict__ params, const TcParams& P, int n) {
+  if (n < 128) {
+    float acc = params[P.b_off[10] + n];
+    for (int j = 0; j < 256; ++j) acc = fmaf(params[P.b_off[9] + j], params[P.w_off[10] + j * 128 + n], acc);
+    return acc;
+  }
+  return n == 128 ? params[P.b_off[8]] : 0.f;
+}
+
+// KIND 0: forward, 1: dgrad, 2: folded inference forward
+template <class Prog, int KIND>
 __device__ __forceinline__ void pack_pair(const float* __restrict__ params, const TcParams& P,
                                           uint8_t* __restrict__ blob, int gtid, int gsz) {
+  auto weight = [&](int s, int k, int n) -> float {
+    if (KIND == 1) return bwd_weight(params, P, s, k, n);
+    if (KIND == 2 && s == 8) return fold_weight(params, P, k, n);
+    return fwd_weight(params, P, s, k, n);   // steps 0..7 of the folded program are the forward's
+  };
   using PL = PairLayout<Prog>;
   for (int v = gtid; v < PL::kBytes / 16; v += gsz) {
     const int byte = v * 16;
@@ -62,15 +90,15 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
       const int k0 = i * kPairK + c * 8, n = cta * half + nl;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float a = FWD ? fwd_weight(params, P, s, k0 + 2 * e, n) : bwd_weight(params, P, s, k0 + 2 * e, n);
-        const float b = FWD ? fwd_weight(params, P, s, k0 + 2 * e + 1, n) : bwd_weight(params, P, s, k0 + 2 * e + 1, n);
-        w[e] = pack_bf16x2(a, b);
+        w[e] = pack_bf16x2(weight(s, k0 + 2 * e, n), weight(s, k0 + 2 * e + 1, n));
       }
     } else {   // bias piece [2 chunks][N/2][8]: k = 15 <- bias[n]
       const int rem = local - 2 * N * ktot, pb = 16 * N;
       const int cta = rem / pb, r2 = rem - cta * pb;
       const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
-      if (cb == 1) w[3] = pack_bf16x2(0.f, params[P.b_off[Prog::layer(s)] + cta * half + nl]);
+      if (cb == 1)
+        w[3] = pack_bf16x2(0.f, (KIND == 2 && s == 8) ? fold_bias(params, P, cta * half + nl)
+                                                      : params[P.b_off[Prog::layer(s)] + cta * half + nl]);
     }
     *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -124,8 +152,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
         make_uint4(pack_bf16x2(W[0], W[1]), pack_bf16x2(W[2], W[3]), pack_bf16x2(W[4], W[5]), pack_bf16x2(W[6], W[7]));
   }
   // pair (cta_group::2) blobs: same weights, K = 64 stages, one contiguous piece per (stage, CTA)
-  pack_pair<FwdProg, true>(params, P, packed + kFwdPairOff, gtid, gsz);
-  pack_pair<BwdProg, false>(params, P, packed + kBwdPairOff, gtid, gsz);
+  pack_pair<FwdProg, 0>(params, P, packed + kFwdPairOff, gtid, gsz);
+  pack_pair<BwdProg, 1>(params, P, packed + kBwdPairOff, gtid, gsz);
+  pack_pair<FwdFoldProg, 2>(params, P, packed + kFoldPairOff, gtid, gsz);
   float* aux = reinterpret_cast<float*>(packed + kAuxOff);
   for (int i = gtid; i < kAuxFloats; i += gsz) {
     const int blk = i >> 8, j = i & 255;
@@ -332,6 +361,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                   const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
                   uint8_t* __restrict__ rec, int ordered) {
   using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
+  // inference with the pair kernels: `features` folded into `rgb_features`, sigma as output column 128 of that
+  // step (tc_layout.cuh FwdFoldProg) -- 9 GEMM steps instead of 10 and no CUDA-core sigma head
+  constexpr bool FOLD = !TRAIN && TWO;
+  using Prog = typename std::conditional<FOLD, FwdFoldProg, FwdProg>::type;
+  constexpr int kLast = Prog::kSteps - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -345,20 +379,20 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
   if (warp == 0) {
     if constexpr (TWO) {
-      if (lane == 0) producer2_role<FwdProg>(sm, packed + kFwdPairOff, cta, n_pairs, first, stride);
+      if (lane == 0) producer2_role<Prog>(sm, packed + (FOLD ? kFoldPairOff : kFwdPairOff), cta, n_pairs, first, stride);
     } else {
       if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
     }
   } else if (warp == 1) {
     if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, 0u, ordered != 0, n_pairs, first, stride);
-      else if (lane == 0) relay_role<FwdProg>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
+      if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 0u, ordered != 0, n_pairs, first, stride);
+      else if (lane == 0) relay_role<Prog>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
     } else {
       if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
     }
   } else if (warp == 11) {
     if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<FwdProg>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
+      if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
     }
   } else if (warp == 10) {
     // ============== record store (training): operand tiles h0..h7, features -> HBM, one bulk copy each ========
@@ -425,7 +459,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
       }
     }
     for (int64_t pair = first; pair < n_pairs; pair += stride) {
-      for (int s = 0; s < FwdProg::kSteps; ++s) {
+      for (int s = 0; s < Prog::kSteps; ++s) {
 #pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = tile_of(pair, tl);
@@ -441,7 +475,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           acc_par[tl] ^= 1;
           tc_fence_after();
 
-          if (s < 9) {
+          if (s < kLast) {
             // hidden layers (ReLU) and `features` (linear): 128 of the 256 columns per thread.  The bias is
             // already in the accumulator (folded into the GEMM), ReLU is fused into the bf16 conversion.
             float dirv[3];
@@ -458,10 +492,10 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             uint8_t* mask_out = (save && s < 8) ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr;
             // three separately instantiated bodies: in one merged loop the compiler if-converts the sigma dot
             // product and runs it on EVERY step (it doubled the epilogue time of the plain ReLU layers)
-            if (s == 7) {
+            if (!FOLD && s == 7) {
               const float sd = epi_hidden<TRAIN, 1>(tacc, sm.hs[tl], h, r, mask_out, head_smem(sm.xs[tl]));
               if (tl == 0) sig_keep0 = sd; else sig_keep1 = sd;   // the halves meet in the s == 9 epilogue
-            } else if (s == 8) {
+            } else if (!FOLD && s == 8) {
               epi_hidden<TRAIN, 2>(tacc, sm.hs[tl], h, r, nullptr, nullptr);
             } else {
               epi_hidden<TRAIN, 0>(tacc, sm.hs[tl], h, r, mask_out, nullptr);
@@ -510,14 +544,22 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
               }
             }
-            const float sig_part = tl == 0 ? sig_keep0 : sig_keep1;
+            float sig_part = tl == 0 ? sig_keep0 : sig_keep1;
+            if (FOLD) {   // sigma pre-activation = accumulator column 128 (bias included)
+              sig_part = 0.f;
+              if (h == 0) {   // warp-uniform
+                float v16[32];
+                tmem_ld32(tmem + lane_base + tl * 256 + 128, v16);   // (columns 144.. are stale: only [0] is used)
+                sig_part = v16[0];
+              }
+            }
             if (h == 1) *reinterpret_cast<float4*>(sm.part[r]) = make_float4(pr, pg, pb, sig_part);
             named_bar_sync(1, kComputeThreads);
             if (h == 0 && valid) {
               const float4 hb = *(reinterpret_cast<const float4*>(head_smem(sm.xs[tl])) + 160);   // b_sigma, b_rgb
               const float4 o4 = *reinterpret_cast<const float4*>(sm.part[r]);
               const float zr = pr + o4.x + hb.y, zg = pg + o4.y + hb.z, zb = pb + o4.z + hb.w;
-              const float sg = fmaxf(sig_part + o4.w + hb.x, 0.f);                         // mlp.py:40
+              const float sg = fmaxf(FOLD ? sig_part : sig_part + o4.w + hb.x, 0.f);       // mlp.py:40
               rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)), sg);
             }
             named_bar_sync(1, kComputeThreads);

@@ -49,6 +49,26 @@ struct FwdProg {
 };
 constexpr int kFwdBlobBytes = FwdProg::blob_off(FwdProg::kSteps);
 
+// ---- inference: `features` folded into `rgb_features`, sigma on the tensor core -------------------------------
+// mlp.py:42-46 applies NO activation between `features` and `rgb_features`, so at inference
+//   G = [h7 W_f + b_f, dir] W_g + b_g = h7 (W_f W_g[:256]) + dir W_g[256:] + (b_f W_g[:256] + b_g)
+// is ONE step from h7 (the product is formed in fp32 when the weights are packed), and sigma = relu(h7 w_s + b_s)
+// rides along as output column 128 of the same step (N = 144).  Saves the 256 x 256 `features` GEMM (11 % of the
+// MACs) and the CUDA-core sigma dot product.  Training keeps the unfolded chain: the weight gradients of
+// `rgb_features` need the `features` activations.  Reported FLOP counts always use the unfolded 593,408 MAC.
+// step:        0    1..4   5      6,7   8
+// layer:       L0   L1-4   L5     L6,7  [rgb_features o features | sigma]
+struct FwdFoldProg {
+  static constexpr int kSteps = 9;
+  static constexpr int kNLast = 144;                 // 128 rgb_features + sigma + 15 zero columns
+  __host__ __device__ static constexpr int layer(int s) { return s; }   // (s < 8; the last step is packed specially)
+  __host__ __device__ static constexpr int nk_h(int s) { return s == 0 ? 0 : 8; }
+  __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 8 ? 1 : 0); }
+  __host__ __device__ static constexpr int N(int s) { return s == 8 ? kNLast : 256; }
+  static constexpr bool kHasBias = true;
+  __host__ __device__ static constexpr int bias_a_chunk(int s) { return s <= 5 ? 6 : 2; }
+};
+
 // ---- backward (dgrad) steps --------------------------------------------------------------------------------
 // step b:      0               1                2 .. 8
 // computes:    dF = dG Wg^T    dZ7 = (dF Wf^T + dsigma Ws^T) * [h7>0]      dZ_{8-b} = (dZ_{9-b} W_{9-b}^T) * [h_{8-b}>0]
@@ -104,7 +124,7 @@ struct PairLayout {
 };
 
 // ---- packed weight buffer ------------------------------------------------------------------------------------
-// [forward blob][dgrad blob][fp32 side table][forward pair blob][dgrad pair blob].  The side table holds 16-byte
+// [forward blob][dgrad blob][fp32 side table][forward pair blob][dgrad pair blob][folded inference pair blob].  The side table holds 16-byte
 // aligned copies (the Keras flat buffer is not aligned: the 1-wide sigma bias shifts everything after it):
 // bias[l] at l*256 (l = 0..11), sigma kernel [256] at 12*256, rgb kernel [128,3] at 13*256.
 constexpr int kBwdBlobOff = kFwdBlobBytes;
@@ -112,7 +132,8 @@ constexpr int kAuxOff = kBwdBlobOff + kBwdBlobBytes;
 constexpr int kAuxFloats = 12 * 256 + 256 + 512;
 constexpr int kFwdPairOff = kAuxOff + kAuxFloats * 4;
 constexpr int kBwdPairOff = kFwdPairOff + PairLayout<FwdProg>::kBytes;
-constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
+constexpr int kFoldPairOff = kBwdPairOff + PairLayout<BwdProg>::kBytes;
+constexpr int kPackedBytes = kFoldPairOff + PairLayout<FwdFoldProg>::kBytes;
 
 struct TcParams {
   int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer

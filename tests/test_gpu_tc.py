@@ -227,8 +227,8 @@ def test_umma_selftest_2cta(N, K):
 def test_tc_pair_kernels_match_single_cta(R, S):
     """The chain kernels run as CTA pairs (cta_group::2 MMAs, K = 64 weight stages) by default; the single-CTA
     kernels (K = 32 stages) are kept behind knerf_debug_tc_variant.  Same bf16 products, same fp32 accumulation
-    order per output element (K ascending, 16 per MMA) -> forward output, saved records and the dgrad record must
-    be bit-identical, weight gradients equal up to the order of the fp32 atomics."""
+    order per output element (K ascending, 16 per MMA) -> training forward output, saved records and the dgrad
+    record must be bit-identical, weight gradients equal up to the order of the fp32 atomics."""
     from keras_nerf_b200 import _lib
     lib = _lib.load()
     _, m = _models(R)
@@ -252,8 +252,12 @@ def test_tc_pair_kernels_match_single_cta(R, S):
     finally:
         lib.knerf_debug_tc_variant(0)
     a, b = res[1], res[3]
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])            # training / inference forward
-    assert torch.equal(a[0], a[1])                                        # saving records does not change the output
+    assert torch.equal(a[0], b[0])                                        # training forward
+    assert torch.equal(a[0], a[1])                                        # single CTA: saving records changes nothing
     assert torch.equal(a[2], b[2])                                        # activation + ReLU' + dZ records
     scale = float(a[3].abs().max())
     assert scale > 0 and float((a[3] - b[3]).abs().max()) <= 1e-5 * scale
+    # The pair kernels' INFERENCE program folds `features` into `rgb_features` and takes sigma from the tensor core
+    # (tc_layout.cuh FwdFoldProg): the same function with one bf16 rounding less -- equal to bf16 tolerance
+    assert float((a[1][..., :3] - b[1][..., :3]).abs().max()) <= 5e-3
+    assert float((a[1][..., 3] - b[1][..., 3]).abs().max()) <= 1e-2 * max(1.0, float(a[1][..., 3].abs().max()))
