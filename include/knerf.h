@@ -196,10 +196,9 @@ int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* strea
  * kernel (mask 1), its weight-gradient kernel (mask 2) or both (3, default) so they can be timed apart.  */
 int knerf_debug_backward_parts(int mask);
 
-/* Diagnostic / A-B measurements: which BF16 chain kernels run.  0 = default (CTA pairs, cta_group::2 MMAs;
- * KNERF_TC_2CTA=0 in the environment selects single CTAs), 1 = single-CTA kernels, 2 = CTA pairs, 3 = CTA
- * pairs whose two MMA-issuing threads keep ring order at inference too (bit-reproducible outputs; training
- * kernels always do).                                                                                       */
+/* Diagnostic: MMA issue order of the BF16 chain kernels.  0 / 2 = default (training kernels issue in ring order
+ * and are bit-reproducible; the inference kernel lets its two MMA-issuing threads interleave: last-bit run-to-run
+ * differences, 16 % more throughput), 3 = ordered issue at inference too.                                   */
 int knerf_debug_tc_variant(int variant);
 
 /* Diagnostic: per-CTA clock64() counters of the BF16 forward kernel (40 uint64 per CTA; slots documented in

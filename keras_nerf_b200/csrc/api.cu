@@ -85,7 +85,8 @@ extern "C" int knerf_debug_backward_parts(int mask) {
 }
 
 extern "C" int knerf_debug_tc_variant(int variant) {
-  tc_set_variant(variant <= 0 ? -1 : variant);
+  KN_CHECK_ARG(variant == 0 || variant == 2 || variant == 3, "knerf_debug_tc_variant: 0 / 2 (default) or 3 (ordered MMA issue)");
+  tc_set_variant(variant);
   return KNERF_OK;
 }
 

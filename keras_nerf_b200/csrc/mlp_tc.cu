@@ -5,22 +5,23 @@
 //
 // Flagship shape only (8x256, skip 4, L = 10/4); other shapes run the fp32 SIMT path.
 //
-// Forward kernel (persistent, 1 CTA / SM, 320 threads):
-//   warp 0      TMA producer: streams the pre-packed bf16 weight blob, 32-wide K stages, 4-slot mbarrier ring
-//   warp 1      MMA issuer:   one thread issues tcgen05.mma (M=128, N=256|128, K=16) and tcgen05.commit
-//   warps 2-9   compute:      PE prologue, TMEM -> register epilogues (bias, ReLU, bf16 pack) that write the
-//                             next layer's A operand straight into shared memory, heads, output.
-//                             Biases ride in the GEMM (constant-1 column, tc_layout.cuh).
+// Forward kernel (persistent CTA pairs, 384 threads per CTA; roles in tc_roles.cuh / tc_roles2.cuh):
+//   warp 0      TMA producer: streams this CTA's half of the pre-packed bf16 weight blob, K = 64 stages, 4-slot ring
+//   warps 1,11  MMA issuers (leader CTA): tcgen05.mma.cta_group::2 (M = 256, N = 256|144, K = 16), alternate items
+//   warps 2-9   compute:      PE prologue, TMEM -> register epilogues (ReLU, bf16 pack) that write the next layer's
+//                             A operand straight into shared memory, rgb head, output.
+//                             Biases ride in the GEMM (constant-1 column, tc_layout.cuh); sigma is column 128 of
+//                             the last step.
+//   warp 10     record store (training): bulk copies of the operand tiles to HBM
 // Each CTA keeps TWO 128-sample tiles in flight (accumulators in TMEM columns [0,256) and [256,512)): while
 // the tensor core runs tile 1's layer, the compute warps drain tile 0's accumulator and build its next A
-// operand, and vice versa, so the MMA pipe only waits when an epilogue is slower than a layer of MMAs.
+// operand, and vice versa.
 // Shared memory: 2 x 64 KB hidden activations + 2 x 16 KB encodings + 4 x 16 KB weight stages = 224 KB.
 #include "mlp_tc.cuh"
 
 #include <cstdlib>
 #include <type_traits>
 
-#include "tc_roles.cuh"
 #include "tc_roles2.cuh"
 
 namespace knerf {
@@ -30,20 +31,15 @@ using namespace tcl;
 namespace {
 
 // ---- weight packing --------------------------------------------------------------------------------------
-// B operand element of forward step s at reduction index k (hs part first, then the encoding part) and output n
+// B operand element of forward step s < 8 at reduction index k (hs part first, then the encoding part), output n
 __device__ __forceinline__ float fwd_weight(const float* __restrict__ params, const TcParams& P, int s, int k, int n) {
-  const int L = FwdProg::layer(s), N = FwdProg::N(s), kh = FwdProg::nk_h(s) * kKStage;
-  const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : (L == 10) ? 283 : 256;
+  const int L = s, kh = FwdProg::nk_h(s) * kKStage;
+  const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : 256;
   const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
-  return row < fan_in ? params[P.w_off[L] + (int64_t)row * N + n] : 0.f;
+  return row < fan_in ? params[P.w_off[L] + (int64_t)row * 256 + n] : 0.f;
 }
-// B operand element of dgrad step b: W[n][k] (n = input feature < 256, k = output feature)
-__device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P, int b, int k, int n) {
-  return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * BwdProg::ld(b) + k];
-}
-
-// last step of the folded inference program (tc_layout.cuh FwdFoldProg): B element at reduction index k (h7 part,
-// then the direction encoding) and output column n; the product W_f W_g is formed here, in fp32
+// last forward step (tc_layout.cuh): reduction index k (h7, then the direction encoding), output column n; the
+// product W' = W_f W_g[:256] is formed here, in fp32
 __device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P, int k, int n) {
   const float* Wf = params + P.w_off[9];    // features      [256, 256]
   const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
@@ -63,17 +59,21 @@ __device__ __forceinline__ float fold_bias(const float* __restrict__ params, con
   }
   return n == 128 ? params[P.b_off[8]] : 0.f;
 }
+// B operand element of dgrad step b: output n = input feature of the layer (< 256), reduction index k = its output
+// feature.  b = 0 goes from d(rgb_features) straight to d(h7): W'[n][k]
+__device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P, int b, int k, int n) {
+  if (b == 0) return fold_weight(params, P, n, k);
+  return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * 256 + k];
+}
 
-// KIND 0: forward, 1: dgrad, 2: folded inference forward
-template <class Prog, int KIND>
+template <class Prog, bool FWD>
 __device__ __forceinline__ void pack_pair(const float* __restrict__ params, const TcParams& P,
                                           uint8_t* __restrict__ blob, int gtid, int gsz) {
-  auto weight = [&](int s, int k, int n) -> float {
-    if (KIND == 1) return bwd_weight(params, P, s, k, n);
-    if (KIND == 2 && s == 8) return fold_weight(params, P, k, n);
-    return fwd_weight(params, P, s, k, n);   // steps 0..7 of the folded program are the forward's
-  };
   using PL = PairLayout<Prog>;
+  auto weight = [&](int s, int k, int n) -> float {
+    if (!FWD) return bwd_weight(params, P, s, k, n);
+    return s == 8 ? fold_weight(params, P, k, n) : fwd_weight(params, P, s, k, n);
+  };
   for (int v = gtid; v < PL::kBytes / 16; v += gsz) {
     const int byte = v * 16;
     int s = 0;
@@ -89,72 +89,23 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
       const int c = r2 / (half * 16), nl = (r2 - c * half * 16) / 16;
       const int k0 = i * kPairK + c * 8, n = cta * half + nl;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        w[e] = pack_bf16x2(weight(s, k0 + 2 * e, n), weight(s, k0 + 2 * e + 1, n));
-      }
+      for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(weight(s, k0 + 2 * e, n), weight(s, k0 + 2 * e + 1, n));
     } else {   // bias piece [2 chunks][N/2][8]: k = 15 <- bias[n]
       const int rem = local - 2 * N * ktot, pb = 16 * N;
       const int cta = rem / pb, r2 = rem - cta * pb;
       const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
       if (cb == 1)
-        w[3] = pack_bf16x2(0.f, (KIND == 2 && s == 8) ? fold_bias(params, P, cta * half + nl)
-                                                      : params[P.b_off[Prog::layer(s)] + cta * half + nl]);
+        w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, cta * half + nl) : params[P.b_off[s] + cta * half + nl]);
     }
     *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
-// forward blob: per step, per K stage: [4 chunks][N][8], element (c, n, e) = W[row(ks, c, e)][n]   (W^T, K-major)
-// dgrad blob:   per step, per K stage: [4 chunks][256][8], element (c, n, e) = W[n][ks*32 + c*8 + e] (W, K-major)
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, TcParams P,
                                                    uint8_t* __restrict__ packed) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  for (int v = gtid; v < kFwdBlobBytes / 16; v += gsz) {
-    int byte = v * 16, s = 0;
-    while (s + 1 < FwdProg::kSteps && byte >= FwdProg::blob_off(s + 1)) ++s;
-    const int local = byte - FwdProg::blob_off(s);
-    const int N = FwdProg::N(s), sb = FwdProg::stage_bytes(s);
-    const int L = FwdProg::layer(s);
-    const int nks = FwdProg::nk_h(s) + FwdProg::nk_x(s);
-    if (local >= nks * sb) {   // bias chunk [2 chunks][N][8]: k = 15 <- bias[n], everything else 0
-      const int rb = local - nks * sb;
-      const int cb = rb / (N * 16), nb = (rb - cb * N * 16) / 16;
-      const uint32_t hi = (cb == 1) ? (pack_bf16x2(0.f, params[P.b_off[L] + nb])) : 0u;
-      *reinterpret_cast<uint4*>(packed + byte) = make_uint4(0u, 0u, 0u, hi);
-      continue;
-    }
-    const int ks = local / sb, r = local - ks * sb;
-    const int c = r / (N * 16), n = (r - c * N * 16) / 16;
-    const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : (L == 10) ? 283 : 256;
-    const float* W = params + P.w_off[L];
-    int row0;
-    if (ks < FwdProg::nk_h(s)) row0 = ks * kKStage + c * 8;
-    else row0 = (FwdProg::nk_h(s) > 0 ? 256 : 0) + (ks - FwdProg::nk_h(s)) * kKStage + c * 8;
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int ra = row0 + 2 * e, rb = ra + 1;
-      const float a = ra < fan_in ? W[(int64_t)ra * N + n] : 0.f;
-      const float b = rb < fan_in ? W[(int64_t)rb * N + n] : 0.f;
-      w[e] = pack_bf16x2(a, b);
-    }
-    *reinterpret_cast<uint4*>(packed + byte) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  for (int v = gtid; v < kBwdBlobBytes / 16; v += gsz) {
-    const int byte = v * 16;
-    int b = 0;
-    while (b + 1 < BwdProg::kSteps && byte >= BwdProg::blob_off(b + 1)) ++b;
-    const int local = byte - BwdProg::blob_off(b);
-    const int ks = local / kStageBytes, r = local - ks * kStageBytes;
-    const int c = r / (256 * 16), n = (r - c * 256 * 16) / 16;
-    const float* W = params + P.w_off[BwdProg::layer(b)] + (int64_t)n * BwdProg::ld(b) + ks * kKStage + c * 8;
-    *reinterpret_cast<uint4*>(packed + kBwdBlobOff + byte) =
-        make_uint4(pack_bf16x2(W[0], W[1]), pack_bf16x2(W[2], W[3]), pack_bf16x2(W[4], W[5]), pack_bf16x2(W[6], W[7]));
-  }
-  // pair (cta_group::2) blobs: same weights, K = 64 stages, one contiguous piece per (stage, CTA)
-  pack_pair<FwdProg, 0>(params, P, packed + kFwdPairOff, gtid, gsz);
-  pack_pair<BwdProg, 1>(params, P, packed + kBwdPairOff, gtid, gsz);
-  pack_pair<FwdFoldProg, 2>(params, P, packed + kFoldPairOff, gtid, gsz);
+  pack_pair<FwdProg, true>(params, P, packed + kFwdPairOff, gtid, gsz);
+  pack_pair<BwdProg, false>(params, P, packed + kBwdPairOff, gtid, gsz);
   float* aux = reinterpret_cast<float*>(packed + kAuxOff);
   for (int i = gtid; i < kAuxFloats; i += gsz) {
     const int blk = i >> 8, j = i & 255;
@@ -301,108 +252,70 @@ __device__ __forceinline__ float* head_smem(uint8_t* xs) { return reinterpret_ca
 
 // ---- epilogue of a hidden step: accumulator -> bf16 A operand of the next step ---------------------------------
 // Thread (row r, half h) converts 128 of the 256 columns, 32 at a time.  The bias is already in the accumulator
-// (folded into the GEMM), ReLU is fused into the bf16 conversion.  KIND 0: ReLU layer (mlp.py:33-34); 1: ReLU
-// layer 7, which also feeds the sigma head -- returns this half-row's part of relu(h7) . W_sigma on the fp32
-// values (mlp.py:40); 2: `features`, linear (mlp.py:42).  mask_out (training, KIND < 2): the ReLU' bits of the
-// tile, 1 bit per activation (tc_layout.cuh kRecMask) for the dgrad kernel.
-template <bool TRAIN, int KIND>
-__device__ __noinline__ float epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
-                                         uint8_t* __restrict__ mask_out, const float* __restrict__ wsig) {
-  float sig[4] = {0.f, 0.f, 0.f, 0.f};   // independent chains: one accumulator serialises 128 dependent FFMAs
+// (folded into the GEMM), ReLU (mlp.py:33-34) is fused into the bf16 conversion.  mask_out (training): the ReLU'
+// bits of the tile, 1 bit per activation (tc_layout.cuh kRecMask) for the dgrad kernel.
+// (__noinline__: one body for all eight layers keeps the kernel below the I-cache thrash point.)
+template <bool TRAIN>
+__device__ __noinline__ void epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
+                                        uint8_t* __restrict__ mask_out) {
 #pragma unroll 1
   for (int gI = 0; gI < 4; ++gI) {
     const int col0 = h * 128 + gI * 32;
     uint32_t v[32];
     tmem_ld32_issue(tacc + col0, v);
-    float4 ws[8];
-    if (KIND == 1) {   // sigma kernel for these 32 columns, fetched while the TMEM load is in flight
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ws[i] = *(reinterpret_cast<const float4*>(wsig + col0) + i);   // shared memory
-    }
     tmem_ld32_wait(v);
     uint32_t mbits = 0u;
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
-      uint4 pk;
-      if (KIND < 2) {
-        pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]), pack_bf16x2_relu(x[4], x[5]),
-                        pack_bf16x2_relu(x[6], x[7]));
-        if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
-          mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
-          mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
-          mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
-          mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
-        }
-      } else {
-        pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-      }
-      if (KIND == 1) {
-        const float4 w0 = ws[2 * c8], w1 = ws[2 * c8 + 1];
-        sig[0] = fmaf(fmaxf(x[0], 0.f), w0.x, sig[0]); sig[1] = fmaf(fmaxf(x[1], 0.f), w0.y, sig[1]);
-        sig[2] = fmaf(fmaxf(x[2], 0.f), w0.z, sig[2]); sig[3] = fmaf(fmaxf(x[3], 0.f), w0.w, sig[3]);
-        sig[0] = fmaf(fmaxf(x[4], 0.f), w1.x, sig[0]); sig[1] = fmaf(fmaxf(x[5], 0.f), w1.y, sig[1]);
-        sig[2] = fmaf(fmaxf(x[6], 0.f), w1.z, sig[2]); sig[3] = fmaf(fmaxf(x[7], 0.f), w1.w, sig[3]);
+      const uint4 pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
+                                  pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
+      if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
+        mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
+        mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
+        mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
+        mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
       }
       // next layer's A operand, in place; when training also the saved record (stored to HBM by warp 10)
       *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
     }
-    if (TRAIN && KIND < 2 && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
+    if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
   }
-  return (sig[0] + sig[1]) + (sig[2] + sig[3]);
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
-// TWO = false: one CTA per SM works alone (cta_group::1).  TWO = true: launched as clusters of 2, the CTA pair
-// shares every weight stage through cta_group::2 MMAs (tc_roles2.cuh); a work unit is then four tiles.
-template <bool TRAIN, bool TWO>
+// Launched as clusters of 2: the CTA pair shares every weight stage through cta_group::2 MMAs (tc_roles2.cuh); a
+// work unit is four tiles (two per CTA).
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o, const float* __restrict__ d,
                   const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
                   uint8_t* __restrict__ rec, int ordered) {
-  using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
-  // inference with the pair kernels: `features` folded into `rgb_features`, sigma as output column 128 of that
-  // step (tc_layout.cuh FwdFoldProg) -- 9 GEMM steps instead of 10 and no CUDA-core sigma head
-  constexpr bool FOLD = !TRAIN && TWO;
-  using Prog = typename std::conditional<FOLD, FwdFoldProg, FwdProg>::type;
+  using Prog = FwdProg;
   constexpr int kLast = Prog::kSteps - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  constexpr int kTilesPerUnit = TWO ? 4 : 2;
-  const int64_t n_pairs = (n_tiles + kTilesPerUnit - 1) / kTilesPerUnit;   // work units (tile pairs / quads)
-  const uint32_t cta = TWO ? cluster_ctarank() : 0u;
-  const int64_t first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
-  uint32_t tmem;
-  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp, cta); else tmem = chain_setup(sm, tid, warp);
+  const int64_t n_pairs = (n_tiles + 3) / 4;   // work units: four tiles per CTA pair
+  const uint32_t cta = cluster_ctarank();
+  const int64_t first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+  const uint32_t tmem = chain2_setup(sm, tid, warp, cta);
+  auto tile_of = [&](int64_t unit, int tl) -> int64_t { return unit * 4 + tl * 2 + (int64_t)cta; };
 
   if (warp == 0) {
-    if constexpr (TWO) {
-      if (lane == 0) producer2_role<Prog>(sm, packed + (FOLD ? kFoldPairOff : kFwdPairOff), cta, n_pairs, first, stride);
-    } else {
-      if (lane == 0) producer_role<FwdProg>(sm, packed, n_pairs);
-    }
+    if (lane == 0) producer2_role<Prog>(sm, packed + kFwdPairOff, cta, n_pairs, first, stride);
   } else if (warp == 1) {
-    if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 0u, ordered != 0, n_pairs, first, stride);
-      else if (lane == 0) relay_role<Prog>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
-    } else {
-      if (lane == 0) mma_role<FwdProg>(sm, tmem, n_pairs);
-    }
+    if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 0u, ordered != 0, n_pairs, first, stride);
+    else if (lane == 0) relay_role<Prog>(sm, n_pairs, first, stride);   // peer CTA: its warp 1 is otherwise idle
   } else if (warp == 11) {
-    if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
-    }
+    if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
   } else if (warp == 10) {
-    // ============== record store (training): operand tiles h0..h7, features -> HBM, one bulk copy each ========
+    // ============== record store (training): the operand tiles h0..h7 -> HBM, bulk copies ======================
     if constexpr (TRAIN) {
       if (lane == 0) {
-        auto tile_of = [&](int64_t unit, int tl) -> int64_t {
-          return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
-        };
-        store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
-                   [&](int item, int64_t tile) { return rec + tile * kRecBytes + (item < 8 ? kRecH0 + item * kHSBytes : kRecF); },
+        store_role(sm, 8, n_tiles, n_pairs, first, stride, tile_of,
+                   [&](int item, int64_t tile) { return rec + tile * kRecBytes + kRecH0 + item * kHSBytes; },
                    [](int) { return (uint32_t)kHSBytes; });
       }
     }
@@ -414,22 +327,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     const int ctid = tid - 64;
     const float* aux = reinterpret_cast<const float*>(packed + kAuxOff);
     uint32_t acc_par[2] = {0, 0};
-    float sig_keep0 = 0.f, sig_keep1 = 0.f;   // this thread's half of the sigma dot product, per tile slot
 
-    auto tile_of = [&](int64_t unit, int tl) -> int64_t {
-      return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
-    };
     uint32_t st_pending = 0, st_par = 0;      // training: bit tl = hs[tl] is being stored / parity of st_done[tl]
     // this thread's (warp's) part of the next A operand is in smem; `record`: the tile is also a saved record
     auto a_ready_arrive = [&](int tl, bool record) {
-      if constexpr (TWO) {
-        a_ready_arrive2(sm, tl, lane);
-      } else {
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(&sm.a_ready[tl]);
-        if (TRAIN) __syncwarp();
-      }
+      a_ready_arrive2(sm, tl, lane);
       if (TRAIN && record) {
         st_ready_arrive(&sm.st_ready[tl], lane);
         st_pending |= 1u << tl;
@@ -468,50 +370,39 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           const bool save = TRAIN && tile < n_tiles;
           uint8_t* rec_t = rec + tile * kRecBytes;
           KN_PROF_BEGIN(t_w);
-          if constexpr (TWO) mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
-          else mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
+          mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
           KN_PROF_END(t_w, 4);
           KN_PROF_BEGIN(t_e);
           acc_par[tl] ^= 1;
           tc_fence_after();
 
           if (s < kLast) {
-            // hidden layers (ReLU) and `features` (linear): 128 of the 256 columns per thread.  The bias is
-            // already in the accumulator (folded into the GEMM), ReLU is fused into the bf16 conversion.
+            // hidden layers: 128 of the 256 columns per thread
             float dirv[3];
             float4 headw = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s == 5) {   // fetched now, used after the epilogue: the L2 latency hides behind it
               load_dir(dirv, d, g, M, S);
-              // head weights -> shared memory (see below): sigma kernel [256] + rgb kernel [128,3] are contiguous
+              // rgb head weights -> shared memory (see below): sigma kernel [256] + rgb kernel [128,3] are contiguous
               if (ctid < 160) headw = __ldg(reinterpret_cast<const float4*>(aux + 12 * 256) + ctid);
               else if (ctid == 160) headw = make_float4(__ldg(aux + 8 * 256), __ldg(aux + 11 * 256), __ldg(aux + 11 * 256 + 1),
                                                         __ldg(aux + 11 * 256 + 2));
             }
             hs_writable(tl);
-            const uint32_t tacc = tmem + lane_base + tl * 256;
-            uint8_t* mask_out = (save && s < 8) ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr;
-            // three separately instantiated bodies: in one merged loop the compiler if-converts the sigma dot
-            // product and runs it on EVERY step (it doubled the epilogue time of the plain ReLU layers)
-            if (!FOLD && s == 7) {
-              const float sd = epi_hidden<TRAIN, 1>(tacc, sm.hs[tl], h, r, mask_out, head_smem(sm.xs[tl]));
-              if (tl == 0) sig_keep0 = sd; else sig_keep1 = sd;   // the halves meet in the s == 9 epilogue
-            } else if (!FOLD && s == 8) {
-              epi_hidden<TRAIN, 2>(tacc, sm.hs[tl], h, r, nullptr, nullptr);
-            } else {
-              epi_hidden<TRAIN, 0>(tacc, sm.hs[tl], h, r, mask_out, nullptr);
-            }
+            epi_hidden<TRAIN>(tmem + lane_base + tl * 256, sm.hs[tl], h, r,
+                              save ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr);
             if (s == 5) {
-              // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for rgb_features
+              // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for the last step
               pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, dirv[0], dirv[1], dirv[2]);
-              // Chunks 4..7 of xs[tl] are dead until the next tile's PE(xyz): they hold the fp32 weights of the two
-              // CUDA-core heads for steps 7 and 9.  (With 227 KB of shared memory the SM has no L1: every __ldg of
-              // these 2.5 KB was an L2 round trip -- 80 per thread and tile.)  Visibility to the other warps: every
-              // warp passes a_ready(5) -> MMA(6) -> acc_ready(6) before anyone reads them.
+              // Chunks 4..7 of xs[tl] are dead until the next tile's PE(xyz): they hold the fp32 weights of the
+              // CUDA-core rgb head for the last step.  (With 227 KB of shared memory the SM has no L1: every __ldg
+              // of them was an L2 round trip.)  Visibility to the other warps: every warp passes a_ready(5) ->
+              // MMA(6) -> acc_ready(6) before anyone reads them.
               if (ctid <= 160) *(reinterpret_cast<float4*>(head_smem(sm.xs[tl])) + ctid) = headw;
             }
             a_ready_arrive(tl, true);
           } else {
-            // rgb_features (bias, linear; mlp.py:43-46) then the rgb head + sigmoid on CUDA cores (mlp.py:48)
+            // columns 0..127: rgb_features (bias included, linear; mlp.py:43-46), then the rgb head + sigmoid on CUDA
+            // cores (mlp.py:48); column 128: the sigma pre-activation (mlp.py:40)
             const int64_t next = pair + stride;
             float nin[3] = {0.f, 0.f, 0.f};   // the next tile of this slot: fetch its sample now, encode it afterwards
             if (next < n_pairs) load_sample(nin, o, d, t, tile_of(next, tl) * kTileM + r, M, S);
@@ -522,7 +413,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               const int col0 = h * 64 + gI * 32;
               uint32_t v[32];
               tmem_ld32_issue(tmem + lane_base + tl * 256 + col0, v);
-              // rgb kernel rows col0..col0+31: 96 consecutive floats, 16-byte aligned; fetched under the TMEM load
+              // rgb kernel rows col0..col0+31: 96 consecutive floats, 16-byte aligned (shared memory)
               float4 wq[24];
 #pragma unroll
               for (int i = 0; i < 24; ++i) wq[i] = *(reinterpret_cast<const float4*>(wrgb + col0 * 3) + i);
@@ -531,7 +422,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = col0 + c8 * 8;
-                const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);   // bias folded, linear (mlp.py:43-46)
+                const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int j = (c8 * 8 + e) * 3;
@@ -544,23 +435,20 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
               }
             }
-            float sig_part = tl == 0 ? sig_keep0 : sig_keep1;
-            if (FOLD) {   // sigma pre-activation = accumulator column 128 (bias included)
-              sig_part = 0.f;
-              if (h == 0) {   // warp-uniform
-                float v16[32];
-                tmem_ld32(tmem + lane_base + tl * 256 + 128, v16);   // (columns 144.. are stale: only [0] is used)
-                sig_part = v16[0];
-              }
+            float sig_pre = 0.f;
+            if (h == 0) {   // warp-uniform
+              float v16[32];
+              tmem_ld32(tmem + lane_base + tl * 256 + 128, v16);   // (columns 144.. are stale: only [0] is used)
+              sig_pre = v16[0];
             }
-            if (h == 1) *reinterpret_cast<float4*>(sm.part[r]) = make_float4(pr, pg, pb, sig_part);
+            if (h == 1) *reinterpret_cast<float4*>(sm.part[r]) = make_float4(pr, pg, pb, 0.f);
             named_bar_sync(1, kComputeThreads);
             if (h == 0 && valid) {
               const float4 hb = *(reinterpret_cast<const float4*>(head_smem(sm.xs[tl])) + 160);   // b_sigma, b_rgb
               const float4 o4 = *reinterpret_cast<const float4*>(sm.part[r]);
               const float zr = pr + o4.x + hb.y, zg = pg + o4.y + hb.z, zb = pb + o4.z + hb.w;
-              const float sg = fmaxf(FOLD ? sig_part : sig_part + o4.w + hb.x, 0.f);       // mlp.py:40
-              rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)), sg);
+              rgbsigma[g] = make_float4(1.f / (1.f + expf(-zr)), 1.f / (1.f + expf(-zg)), 1.f / (1.f + expf(-zb)),
+                                        fmaxf(sig_pre, 0.f));
             }
             named_bar_sync(1, kComputeThreads);
             tc_fence_before();
@@ -574,24 +462,17 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     KN_PROF_END(t_c, 5);
     if (tid == 64) { KN_PROF_FLUSH(); }
   }
-  if constexpr (TWO) chain2_teardown(tmem, warp); else chain_teardown(tmem, warp);
+  chain2_teardown(tmem, warp);
 }
 
 }  // namespace
 
 bool tc_path_compiled() { return true; }
 
-// Which chain-kernel variant runs: CTA pairs (cta_group::2, default) or single CTAs.  KNERF_TC_2CTA=0 in the
-// environment or knerf_debug_tc_variant(1) selects the single-CTA kernels (kept for A/B measurements and tests).
-static int g_tc_variant = -1;
+// knerf_debug_tc_variant(3): the two MMA-issuing threads keep ring order at inference too (bit-reproducible
+// outputs; training kernels always do).  0 / 2: default.
+static int g_tc_variant = 0;
 void tc_set_variant(int v) { g_tc_variant = v; }
-bool tc_use_pairs() {
-  if (g_tc_variant < 0) {
-    const char* e = std::getenv("KNERF_TC_2CTA");
-    g_tc_variant = (e != nullptr && e[0] == '0') ? 1 : 2;
-  }
-  return g_tc_variant >= 2;
-}
 bool tc_ordered_issue() { return g_tc_variant == 3; }
 
 // diagnostic (-DKNERF_TC_TIMING builds only): copy and clear the forward kernel's per-CTA cycle counters
@@ -613,7 +494,7 @@ int64_t tc_packed_weight_bytes(const Model& m) { return is_flagship(m) ? kPacked
 int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training) {
   if (!is_flagship(m)) return -1;
   if (!training) return 256;
-  return cdiv(rows, kTileM) * (int64_t)(kRecBytes + kDzBytes) + 256;
+  return kXBytes + cdiv(rows, kTileM) * (int64_t)(kRecBytes + kDzBytes) + 256;
 }
 
 TcParams tc_make_params(const Model& m) {
@@ -643,40 +524,29 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
                "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");
   KN_CHECK_ARG(M < (int64_t(1) << 31), "tc_forward: at most 2^31 - 1 samples per call");
   const int64_t n_tiles = cdiv(M, kTileM);
-  const bool two = tc_use_pairs() && n_tiles >= 4;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);
   cfg.stream = st;
-  if (two) {
-    const int64_t n_quads = cdiv(n_tiles, 4);
-    cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(n_quads, kNumSMs / 2)));
-    cfg.dynamicSmemBytes = sizeof(Chain2Smem);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3((unsigned)std::min<int64_t>(cdiv(n_tiles, 2), kNumSMs));
-    cfg.dynamicSmemBytes = sizeof(ChainSmem);
-  }
-  // MMA issue order of the pair kernels (tc_roles2.cuh): bit-reproducible when training, free-running at
-  // inference unless knerf_debug_tc_variant(3) asks for the ordered form
+  cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(cdiv(n_tiles, 4), kNumSMs / 2)));
+  cfg.dynamicSmemBytes = sizeof(ChainSmem);
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // MMA issue order (tc_roles2.cuh): bit-reproducible when training, free-running at inference unless
+  // knerf_debug_tc_variant(3) asks for the ordered form
   const int ordered = (training || tc_ordered_issue()) ? 1 : 0;
   const uint8_t* pk = (const uint8_t*)packed;
   float4* out = (float4*)rgbsigma;
-  uint8_t* rec = training ? (uint8_t*)ws : nullptr;
-#define KN_LAUNCH_FWD(TR, TW)                                                                                       \
-  do {                                                                                                              \
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<TR, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                 (int)cfg.dynamicSmemBytes));                                                       \
-    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<TR, TW>, pk, o, d, t, M, S, out, rec, ordered));                       \
-  } while (0)
-  if (training && two) KN_LAUNCH_FWD(true, true);
-  else if (training) KN_LAUNCH_FWD(true, false);
-  else if (two) KN_LAUNCH_FWD(false, true);
-  else KN_LAUNCH_FWD(false, false);
-#undef KN_LAUNCH_FWD
+  uint8_t* rec = training ? (uint8_t*)ws + kXBytes : nullptr;
+  if (training) {
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<true>, pk, o, d, t, M, S, out, rec, ordered));
+  } else {
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<false>, pk, o, d, t, M, S, out, rec, ordered));
+  }
   KN_LAUNCH_CHECK();
   return KNERF_OK;
 }

@@ -16,9 +16,8 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
                 float* grads, char* ws, int64_t ws_bytes, cudaStream_t st);
 
 void tc_set_backward_parts(int mask);
-void tc_set_variant(int v);   // 0/-1 = default (env), 1 = single-CTA kernels, 2 = CTA pairs, 3 = pairs, ordered MMA issue
+void tc_set_variant(int v);   // 0 / 2 = default, 3 = ordered MMA issue at inference too
 bool tc_ordered_issue();
-bool tc_use_pairs();
 int tc_debug_timing(unsigned long long* host_out, int n);
 
 }  // namespace knerf

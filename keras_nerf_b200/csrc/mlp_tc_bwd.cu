@@ -1,18 +1,18 @@
 // a11 (KNERF_BF16 mode): backward of the NeRF MLP on tcgen05 tensor cores.
 //
-//  1. tc_mlp_dgrad_kernel -- the forward's chain structure run backwards: starting from the gradient w.r.t. the
-//     head pre-activations (from the fused compositing backward) it walks rgb_features -> features/sigma ->
-//     layer 7 .. layer 1, each step one [128 x 256] x [256 x 256] tcgen05 GEMM against W^T followed by a
-//     ReLU-mask epilogue (mask = saved forward activation > 0).  Every pre-activation gradient tile dZ_l is
-//     written once to HBM in chunk-major bf16 for step 2; bias gradients are the column sums of the same tiles.
+//  1. tc_mlp_dgrad_kernel -- the forward's chain structure run backwards (same CTA-pair roles): starting from the
+//     gradient w.r.t. the head pre-activations (from the fused compositing backward) it goes from d(rgb_features)
+//     straight to d(h7) through W'^T (tc_layout.cuh: `features` is folded away), then layer 7 .. layer 1, each step
+//     one [128 x 256] x [256 x 256] GEMM followed by a ReLU' epilogue (1-bit masks written by the forward).
+//     Every pre-activation gradient tile dZ_l is written once to HBM in chunk-major bf16 for step 2.
 //     No gradient flows into the xyz / direction encodings (mlp.py inputs are constants: nerf.py:361-369).
 //  2. tc_wgrad_kernel -- dW_l = X_l^T dZ_l with the reduction over SAMPLES: the saved activation / gradient
 //     blobs are consumed as MN-major UMMA operands (same bytes, other axis; see tc_ptx.cuh), fp32 partial
-//     sums stay in TMEM across all tiles of a work item and are flushed once with red.global.add.f32.
+//     sums stay in TMEM across all tiles of a work item and are flushed once with red.global.add.f32; idle warps
+//     take the bias gradients (column sums of the dZ units in shared memory).
+//  3. tc_finish_kernel -- the weight gradients of `features` and of the first 256 rows of `rgb_features` from
+//     X = h7^T dG (tc_layout.cuh), a 256 x 256 x 128 problem once per call.
 #include "mlp_tc.cuh"
-#include <type_traits>
-
-#include "tc_roles.cuh"
 #include "tc_roles2.cuh"
 
 namespace knerf {
@@ -27,11 +27,11 @@ namespace {
 // dgrad chain
 // =============================================================================================================
 // epilogue of one dgrad step: accumulator (dH = dZ_next W^T) -> pre-activation gradient tile, bf16.
-// KIND 0: d(features), linear, no mask;  1: dZ7 = (dH + d(sigma_pre) Ws^T) * ReLU'(h7) -- the sigma head shares h7
-// with `features`;  2: dZ_l = dH * ReLU'(h_l), l = 6..1;  3: dZ0, the last step: feeds no further GEMM, so it goes
-// to HBM directly (dst = record or nullptr) and must NOT touch hs[tl], which the other half-row thread of this
-// row may already be rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10)
-// the dZ record.  mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
+// KIND 1: dZ7 = (dG W'^T + d(sigma_pre) Ws^T) * ReLU'(h7) -- the sigma head hangs off h7 too;
+// 2: dZ_l = dH * ReLU'(h_l), l = 6..1;  3: dZ0, the last step: feeds no further GEMM, so it goes to HBM directly
+// (dst = record or nullptr) and must NOT touch hs[tl], which the other half-row thread of this row may already be
+// rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10) the dZ record.
+// mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
 template <int KIND>
 __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, uint4 mbv, float dsig,
                                        const float* __restrict__ wsig) {
@@ -71,68 +71,41 @@ __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst,
   }
 }
 
-// TWO = false: one CTA per SM works alone.  TWO = true: clusters of 2, cta_group::2 MMAs (tc_roles2.cuh); a work
-// unit is then four tiles (two per CTA).
-template <bool TWO>
+// clusters of 2, cta_group::2 MMAs (tc_roles2.cuh); a work unit is four tiles (two per CTA)
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict__ d_pre, int64_t M,
                     const uint8_t* __restrict__ rec, uint8_t* __restrict__ dz, float* __restrict__ grads, TcParams P) {
-  using Smem = typename std::conditional<TWO, Chain2Smem, ChainSmem>::type;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (M + kTileM - 1) / kTileM;
-  constexpr int kTilesPerUnit = TWO ? 4 : 2;
-  const int64_t n_pairs = (n_tiles + kTilesPerUnit - 1) / kTilesPerUnit;   // work units (tile pairs / quads)
-  const uint32_t cta = TWO ? cluster_ctarank() : 0u;
-  const int64_t first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
-  uint32_t tmem;
-  if constexpr (TWO) tmem = chain2_setup(sm, tid, warp, cta); else tmem = chain_setup(sm, tid, warp);
+  const int64_t n_pairs = (n_tiles + 3) / 4;   // work units: four tiles per CTA pair
+  const uint32_t cta = cluster_ctarank();
+  const int64_t first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+  const uint32_t tmem = chain2_setup(sm, tid, warp, cta);
+  auto tile_of = [&](int64_t unit, int tl) -> int64_t { return unit * 4 + tl * 2 + (int64_t)cta; };
 
   if (warp == 0) {
-    if constexpr (TWO) {
-      if (lane == 0) producer2_role<BwdProg>(sm, packed + kBwdPairOff, cta, n_pairs, first, stride);
-    } else {
-      if (lane == 0) producer_role<BwdProg>(sm, packed + kBwdBlobOff, n_pairs);
-    }
+    if (lane == 0) producer2_role<BwdProg>(sm, packed + kBwdPairOff, cta, n_pairs, first, stride);
   } else if (warp == 1) {
-    if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 0u, true, n_pairs, first, stride);
-      else if (lane == 0) relay_role<BwdProg>(sm, n_pairs, first, stride);
-    } else {
-      if (lane == 0) mma_role<BwdProg>(sm, tmem, n_pairs);
-    }
+    if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 0u, true, n_pairs, first, stride);
+    else if (lane == 0) relay_role<BwdProg>(sm, n_pairs, first, stride);
   } else if (warp == 11) {
-    if constexpr (TWO) {
-      if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 1u, true, n_pairs, first, stride);
-    }
+    if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 1u, true, n_pairs, first, stride);
   } else if (warp == 10) {
     // record store: every A operand of the chain is also a dZ record for the weight-gradient kernel -- item 0 = dG
-    // (prologue, 128 columns), item 1 = dF, items 2..8 = dZ7..dZ1; one bulk copy each (tc_roles.cuh store_role)
+    // (prologue, 128 columns), items 1..7 = dZ7..dZ1 (tc_roles.cuh store_role)
     if (lane == 0) {
-      auto tile_of = [&](int64_t unit, int tl) -> int64_t {
-        return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
-      };
-      store_role(sm, 9, n_tiles, n_pairs, first, stride, tile_of,
+      store_role(sm, 8, n_tiles, n_pairs, first, stride, tile_of,
                  [&](int item, int64_t tile) {
-                   return dz + tile * kDzBytes + (item == 0 ? kDzG : item == 1 ? kDzF : kDzZ0 + (9 - item) * kHSBytes);
+                   return dz + tile * kDzBytes + (item == 0 ? kDzG : kDzZ0 + (8 - item) * kHSBytes);
                  },
                  [](int item) { return (uint32_t)(item == 0 ? 32768 : kHSBytes); });
     }
   } else {
-    auto tile_of = [&](int64_t unit, int tl) -> int64_t {
-      return TWO ? unit * 4 + tl * 2 + (int64_t)cta : unit * 2 + tl;
-    };
     uint32_t st_pending = 0, st_par = 0;      // bit tl = hs[tl] is being stored / parity of st_done[tl]
     auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand (= dZ record) is in smem
-      if constexpr (TWO) {
-        a_ready_arrive2(sm, tl, lane);
-      } else {
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(&sm.a_ready[tl]);
-        __syncwarp();
-      }
+      a_ready_arrive2(sm, tl, lane);
       st_ready_arrive(&sm.st_ready[tl], lane);
       st_pending |= 1u << tl;
     };
@@ -210,22 +183,22 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     }
     for (int64_t pair = first; pair < n_pairs; pair += stride) {
       for (int b = 0; b < BwdProg::kSteps; ++b) {
-        const int zi = 8 - b;                                  // index of the dZ this step produces (b >= 1)
+        const int zi = 7 - b;                                  // index of the dZ this step produces
 #pragma unroll 1
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = tile_of(pair, tl);
           const bool active = tile < n_tiles;
-          uint8_t* out = dz + tile * kDzBytes + (b == 0 ? kDzF : kDzZ0 + zi * kHSBytes);
+          uint8_t* out = dz + tile * kDzBytes + kDzZ0 + zi * kHSBytes;
           const uint8_t* mask = rec + tile * kRecBytes + kRecMask + zi * kMaskLayerBytes;
           const float dsig = tl == 0 ? dsig_keep0 : dsig_keep1;
           // the ReLU' bits (written by the forward, 1 bit per activation) do not depend on the accumulator: fetch
           // this thread's 4 x 32 columns BEFORE waiting for the MMA so that the latency overlaps it
           uint32_t mb[4] = {0u, 0u, 0u, 0u};
-          if (b >= 1 && active) {
+          if (active) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) mb[i] = __ldg(reinterpret_cast<const uint32_t*>(mask + (h * 4 + i) * 512 + r * 4));
           }
-          mbar_wait(&sm.acc_ready[tl], acc_par[tl]);
+          mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;
           tc_fence_after();
           if (b + 1 < BwdProg::kSteps) hs_writable(tl);
@@ -233,8 +206,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           // would run on every step)
           const uint32_t tacc = tmem + lane_base + tl * 256;
           const uint4 mbv = make_uint4(mb[0], mb[1], mb[2], mb[3]);
-          if (b == 0) epi_dgrad<0>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr);
-          else if (b == 1) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig);
+          if (b == 0) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig);
           else if (b + 1 < BwdProg::kSteps) epi_dgrad<2>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr);
           else epi_dgrad<3>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr);
           if (b + 1 < BwdProg::kSteps) {
@@ -249,7 +221,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       }
     }
   }
-  if constexpr (TWO) chain2_teardown(tmem, warp); else chain_teardown(tmem, warp);
+  chain2_teardown(tmem, warp);
 }
 
 // =============================================================================================================
@@ -258,13 +230,15 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
 constexpr int kWUnitBytes = 32768;     // 16 chunks x 128 samples x 16 B: 128 features (A) or 128 outputs (B)
 constexpr int kWSlots = 6;
 constexpr int kWThreads = 192;         // warp 0 producer, warp 1 MMA, warps 2-5 flush
-constexpr int kNumTasks = 13;
+constexpr int kNumTasks = 10;
+constexpr int kWMaxUnits = 6;
 
 struct WUnit { int src, off, bytes, bias_layer, bias_col0; };   // src 0 = forward record, 1 = dz record;
                                                                 // bias_layer >= 0: column sums of this dZ unit are db
 struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b; };
-struct WTask { int n_units; WUnit u[4]; int n_groups; WGroup g[4]; int cost; };
+struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; };
 // mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
+//      3: X = h7^T dG into the fp32 scratch (tc_finish_kernel turns it into dW_features and dW_rgb_features[:256])
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
@@ -299,28 +273,26 @@ static WTaskTable build_task_table() {
   xpart(0, kDzZ0, 0);                                                        // layer 0
   for (int l = 1; l <= 7; ++l) big(l, kRecH0 + (l - 1) * kHSBytes, kDzZ0 + l * kHSBytes, 0);   // layers 1..7 (h part)
   xpart(5, kDzZ0 + 5 * kHSBytes, 256);                                       // layer 5, skip rows 256..318
-  big(9, kRecH0 + 7 * kHSBytes, kDzF, 0);                                    // features
-  {  // sigma (A = h7 halves) and rgb (A = rgb_features) against the packed d_pre operand (N = 16)
+  {  // everything that hangs off h7 and d(rgb_features): h7 is read ONCE for X = h7^T dG (-> features and
+     // rgb_features[:256], tc_finish_kernel) and for the sigma kernel; the direction rows of rgb_features and the
+     // rgb kernel (A = rgb_features activations, B = the packed d_pre operand, N = 16) ride along.
+     // Units in order of first use; groups ordered so that each unit is released as early as possible.
     WTask& t = T.t[n++];
-    t.n_units = 4;
-    t.u[0] = {1, kDzP, 4096, -1, 0}; t.u[1] = {0, kRecH0 + 7 * kHSBytes, kWUnitBytes, -1, 0};
-    t.u[2] = {0, kRecH0 + 7 * kHSBytes + kWUnitBytes, kWUnitBytes, -1, 0}; t.u[3] = {0, kRecG, kWUnitBytes, -1, 0};
-    t.n_groups = 3;
-    t.g[0] = {1, 0, 0, 16, 8, 0, 128, 0, 1, 1, 0};
-    t.g[1] = {2, 0, 32, 16, 8, 128, 128, 0, 1, 1, 0};
-    t.g[2] = {3, 0, 64, 16, 11, 0, 128, 0, 2, 1, 1};
-    t.cost = 100;
-  }
-  {  // rgb_features: A = features halves + PE(dir) (27 valid rows), B = dG (N = 128)
-    WTask& t = T.t[n++];
-    t.n_units = 4;
-    t.u[0] = {1, kDzG, kWUnitBytes, 10, 0}; t.u[1] = {0, kRecF, kWUnitBytes, -1, 0};
-    t.u[2] = {0, kRecF + kWUnitBytes, kWUnitBytes, -1, 0};
-    t.u[3] = {0, kRecDS, 8192, -1, 0};   // PE(dir): 32 columns = 8 KB (27 valid rows of the accumulator)
-    t.n_groups = 3;
-    t.g[0] = {1, 0, 0, 128, 10, 0, 128, 0, 0, 1, 0};
-    t.g[1] = {2, 0, 128, 128, 10, 128, 128, 0, 0, 1, 0};
-    t.g[2] = {3, 0, 256, 128, 10, 256, 27, 0, 0, 1, 1};
+    const int h7 = kRecH0 + 7 * kHSBytes;
+    t.n_units = 6;
+    t.u[0] = {0, h7, kWUnitBytes, -1, 0};                 // h7 features 0..127
+    t.u[1] = {1, kDzG, kWUnitBytes, 10, 0};               // dG (its column sums = db_rgb_features)
+    t.u[2] = {1, kDzP, 4096, -1, 0};                      // (d rgb_pre, d sigma_pre)
+    t.u[3] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0};   // h7 features 128..255
+    t.u[4] = {0, kRecDS, 8192, -1, 0};                    // PE(dir): 32 columns = 8 KB (27 valid accumulator rows)
+    t.u[5] = {0, kRecG, kWUnitBytes, -1, 0};              // rgb_features activations
+    t.n_groups = 6;
+    t.g[0] = {0, 1, 0, 128, -1, 0, 128, 0, 3, 0, 0};
+    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0};
+    t.g[2] = {3, 1, 128, 128, -1, 128, 128, 0, 3, 0, 0};
+    t.g[3] = {3, 2, 400, 16, 8, 128, 128, 0, 1, 1, 0};
+    t.g[4] = {4, 1, 256, 128, 10, 256, 27, 0, 0, 1, 1};
+    t.g[5] = {5, 2, 416, 16, 11, 0, 128, 0, 2, 1, 1};
     t.cost = 128;
   }
   return T;
@@ -360,8 +332,8 @@ static int count_items(const WTaskTable& T, int slabs_per_cost_x128) {
 
 __global__ void __launch_bounds__(kWThreads, 1)
 tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz, int64_t n_tiles,
-                float* __restrict__ grads, TcParams P, const __grid_constant__ WTaskTable T, int n_items,
-                int slabs) {
+                float* __restrict__ grads, float* __restrict__ xbuf, TcParams P, const __grid_constant__ WTaskTable T,
+                int n_items, int slabs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -485,6 +457,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + fc * 8;
 #pragma unroll
             for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e]);
+            if (t.u[k].bias_layer == 10) {   // sum(dG) of THIS call, for tc_finish_kernel
+#pragma unroll
+              for (int e = 0; e < 8; ++e) atomicAdd(xbuf + 256 * 128 + t.u[k].bias_col0 + fc * 8 + e, a[e]);
+            }
           }
           ++nb;
         }
@@ -502,6 +478,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             if (g.mode == 0) {
               const int ld = (g.layer == 10) ? 128 : 256;
               float* dst = grads + P.w_off[g.layer] + (int64_t)(g.row_base + row) * ld + g.col_base + c0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+            } else if (g.mode == 3) {
+              float* dst = xbuf + (int64_t)(g.row_base + row) * 128 + c0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
             } else if (g.mode == 1) {
@@ -522,15 +502,51 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// =============================================================================================================
+// features / rgb_features weight gradients from X = h7^T dG (tc_layout.cuh)
+// =============================================================================================================
+//   dW_f[i][j]      += sum_n X[i][n] W_g[j][n]                         (i, j < 256; W_g = rgb_features kernel [283,128])
+//   dW_g[j][n]      += sum_i W_f[i][j] X[i][n] + b_f[j] s[n]           (j < 256, n < 128; s = sum(dG) of this call)
+//   db_f[j]         += sum_n s[n] W_g[j][n]
+// One thread per output element; 12.6 M MAC per call, operands (384 KB) stay in L2.
+__global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict__ params, TcParams P,
+                                                        const float* __restrict__ xbuf, float* __restrict__ grads) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Wf = params + P.w_off[9];
+  const float* Wg = params + P.w_off[10];
+  const float* s = xbuf + 256 * 128;
+  if (idx < 256 * 256) {
+    const int i = idx >> 8, j = idx & 255;
+    const float* x = xbuf + i * 128;
+    const float* w = Wg + j * 128;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < 128; ++n) acc = fmaf(x[n], w[n], acc);
+    grads[P.w_off[9] + idx] += acc;
+  } else if (idx < 256 * 256 + 256 * 128) {
+    const int e = idx - 256 * 256, j = e >> 7, n = e & 127;
+    float acc = params[P.b_off[9] + j] * s[n];
+#pragma unroll 8
+    for (int i = 0; i < 256; ++i) acc = fmaf(Wf[i * 256 + j], xbuf[i * 128 + n], acc);
+    grads[P.w_off[10] + e] += acc;
+  } else if (idx < 256 * 256 + 256 * 128 + 256) {
+    const int j = idx - (256 * 256 + 256 * 128);
+    const float* w = Wg + j * 128;
+    float acc = 0.f;
+    for (int n = 0; n < 128; ++n) acc = fmaf(s[n], w[n], acc);
+    grads[P.b_off[9] + j] += acc;
+  }
+}
+
 }  // namespace
 
-// diagnostic: which of the two backward kernels knerf_mlp_backward launches in BF16 mode (bit 0 dgrad, bit 1 wgrad)
+// diagnostic: which of the backward kernels knerf_mlp_backward launches in BF16 mode (bit 0 dgrad, bit 1 wgrad +
+// finish)
 static thread_local int g_bwd_parts = 3;
 void tc_set_backward_parts(int mask) { g_bwd_parts = mask & 3; }
 
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
-  (void)params;
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
@@ -539,46 +555,41 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
                 (long long)tc_workspace_bytes(m, M, true));
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_pre) & 15) == 0, "tc_backward: d_pre must be 16-byte aligned");
   const int64_t n_tiles = cdiv(M, kTileM);
-  uint8_t* rec = (uint8_t*)ws;
+  float* xbuf = (float*)ws;                                // X = h7^T dG and sum(dG) of this call
+  uint8_t* rec = (uint8_t*)ws + kXBytes;
   uint8_t* dz = rec + n_tiles * (int64_t)kRecBytes;
   const TcParams P = tc_make_params(m);
 
   if (g_bwd_parts & 1) {
-    const bool two = tc_use_pairs() && n_tiles >= 4;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     cfg.blockDim = dim3(kThreads);
     cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(cdiv(n_tiles, 4), kNumSMs / 2)));
+    cfg.dynamicSmemBytes = sizeof(ChainSmem);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     const uint8_t* pk = (const uint8_t*)packed;
     const float4* dp = (const float4*)d_pre;
     const uint8_t* rec_c = rec;
-    if (two) {
-      cfg.gridDim = dim3((unsigned)(2 * std::min<int64_t>(cdiv(n_tiles, 4), kNumSMs / 2)));
-      cfg.dynamicSmemBytes = sizeof(Chain2Smem);
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)cfg.dynamicSmemBytes));
-      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<true>, pk, dp, M, rec_c, dz, grads, P));
-    } else {
-      cfg.gridDim = dim3((unsigned)std::min<int64_t>(cdiv(n_tiles, 2), kNumSMs));
-      cfg.dynamicSmemBytes = sizeof(ChainSmem);
-      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)cfg.dynamicSmemBytes));
-      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<false>, pk, dp, M, rec_c, dz, grads, P));
-    }
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel, pk, dp, M, rec_c, dz, grads, P));
     KN_LAUNCH_CHECK();
   }
   if (g_bwd_parts & 2) {
-    static const WTaskTable h_table = build_task_table();   // ~3 KB, passed by value as a __grid_constant__
-    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(26, n_tiles / 4));
+    static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
+    // items ~ 2 x 148: 8 tasks of cost 128 and 2 of cost 96 -> 8 s + 2 * (3 s / 4) items for s slabs
+    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
     const int grid = std::min(n_items, kNumSMs);
     const size_t smem = sizeof(WSmem);
+    KN_CUDA(cudaMemsetAsync(xbuf, 0, kXFloats * sizeof(float), st));
     KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, P, h_table, n_items, slabs);
+    tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
+    KN_LAUNCH_CHECK();
+    tc_finish_kernel<<<(256 * 256 + 256 * 128 + 256 + 255) / 256, 256, 0, st>>>(params, P, xbuf, grads);
     KN_LAUNCH_CHECK();
   }
   return KNERF_OK;

@@ -7,93 +7,65 @@
 namespace knerf {
 namespace tcl {
 
-constexpr int kTileM = 128;                        // samples per tile (UMMA M)
+constexpr int kTileM = 128;                        // samples per tile (UMMA M per CTA)
 constexpr int kU = 256;
-constexpr int kKStage = 32;                        // K elements per weight stage
-constexpr int kStageBytes = kU * kKStage * 2;      // 16 KB (N = 256); N = 128 stages use half
-constexpr int kNumStages = 4;
+constexpr int kKStage = 32;                        // granularity of the K tables below (nk_h / nk_x count 32-wide blocks)
 constexpr int kHSBytes = kTileM * kU * 2;          // 64 KB: one [128 x 256] bf16 operand, chunk-major
 constexpr int kXSBytes = kTileM * 64 * 2;          // 16 KB
 constexpr int kChunkA = kTileM * 16;               // bytes between 8-element chunks of a 128-row operand (2048)
 constexpr int kThreads = 384;                      // warps: 0 TMA producer, 1 MMA issuer (even ring items) / relay,
                                                    // 2-9 compute, 10 record store (training kernels), 11 MMA issuer of
-                                                   // the odd ring items (pair kernels, leader CTA).  12 warps: a 13th
-                                                   // would cap ptxas at 128 registers and spill (no L1 here: a spill
-                                                   // is an L2 round trip)
+                                                   // the odd ring items (leader CTA).  12 warps: a 13th would cap ptxas
+                                                   // at 128 registers and spill (no L1 here: a spill is an L2 trip)
 constexpr int kComputeThreads = 256;
 
 // ---- forward steps ---------------------------------------------------------------------------------------
-// step:        0    1..4   5      6,7   8          9
-// layer:       L0   L1-4   L5     L6,7  features   rgb_features      (sigma and rgb heads run on CUDA cores)
+// mlp.py:42-46 applies NO activation between `features` and `rgb_features`, so
+//   G = [h7 W_f + b_f, dir] W_g + b_g = h7 (W_f W_g[:256]) + dir W_g[256:] + (b_f W_g[:256] + b_g)
+// is ONE step from h7 (the product W' = W_f W_g[:256] is formed in fp32 when the weights are packed), and
+// sigma = relu(h7 w_s + b_s) rides along as output column 128 of the same step (N = 144).  Saves the 256 x 256
+// `features` GEMM (11 % of the MACs), its 64 KB/tile activation record and the CUDA-core sigma dot product.
+// The backward pass never needs the `features` activations either: with X = h7^T dG (one weight-gradient GEMM)
+//   dW_f = X W_g[:256]^T,   dW_g[:256] = W_f^T X + b_f (x) sum(dG),   db_f = sum(dG) W_g[:256]^T
+// (tc_finish_kernel, once per backward call), and the dgrad chain goes from dG to d(h7) through W'^T directly.
+// Reported FLOP counts always use the unfolded 593,408 MAC per sample.
+// step:        0    1..4   5      6,7   8
+// layer:       L0   L1-4   L5     L6,7  [rgb_features o features | sigma]       (rgb head: CUDA cores)
 struct FwdProg {
-  static constexpr int kSteps = 10;
-  __host__ __device__ static constexpr int layer(int s) { return s < 8 ? s : (s == 8 ? 9 : 10); }
-  __host__ __device__ static constexpr int nk_h(int s) { return s == 0 ? 0 : 8; }   // K stages fed by hs
-  __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 9 ? 1 : 0); }
-  __host__ __device__ static constexpr int N(int s) { return s == 9 ? 128 : 256; }
-  __host__ __device__ static constexpr int stage_bytes(int s) { return N(s) * kKStage * 2; }
+  static constexpr int kSteps = 9;
+  static constexpr int kNLast = 144;                 // 128 rgb_features + sigma + 15 zero columns
+  __host__ __device__ static constexpr int layer(int s) { return s; }   // (s < 8; the last step is packed specially)
+  __host__ __device__ static constexpr int nk_h(int s) { return s == 0 ? 0 : 8; }   // 32-wide K blocks fed by hs
+  __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 8 ? 1 : 0); }
+  __host__ __device__ static constexpr int N(int s) { return s == 8 ? kNLast : 256; }
   // Bias folded into the GEMM: every step ends with ONE extra K=16 MMA whose A operand is two chunks of the
   // encoding buffer that contain a constant-1 column (PE(xyz) pad column 63 for steps 0..5, PE(dir) pad column
   // 31 afterwards) and whose B operand [2 chunks][N][8] is zero except k = 15 <- bias[n].  The real weight rows
   // of those pad columns are zero, so the 1.0 never leaks into the ordinary stages.  Costs 1/16 more MMA time,
   // removes every bias load and add from the epilogue (which is the critical path).
   static constexpr bool kHasBias = true;
-  __host__ __device__ static constexpr int bias_bytes(int s) { return N(s) * 32; }
-  __host__ __device__ static constexpr int bias_a_chunk(int s) { return s <= 5 ? 6 : 2; }
-  __host__ __device__ static constexpr int step_bytes(int s) { return (nk_h(s) + nk_x(s)) * stage_bytes(s) + bias_bytes(s); }
-  __host__ __device__ static constexpr int blob_off(int s) {
-    int off = 0;
-    for (int i = 0; i < s; ++i) off += step_bytes(i);
-    return off;
-  }
-};
-constexpr int kFwdBlobBytes = FwdProg::blob_off(FwdProg::kSteps);
-
-// ---- inference: `features` folded into `rgb_features`, sigma on the tensor core -------------------------------
-// mlp.py:42-46 applies NO activation between `features` and `rgb_features`, so at inference
-//   G = [h7 W_f + b_f, dir] W_g + b_g = h7 (W_f W_g[:256]) + dir W_g[256:] + (b_f W_g[:256] + b_g)
-// is ONE step from h7 (the product is formed in fp32 when the weights are packed), and sigma = relu(h7 w_s + b_s)
-// rides along as output column 128 of the same step (N = 144).  Saves the 256 x 256 `features` GEMM (11 % of the
-// MACs) and the CUDA-core sigma dot product.  Training keeps the unfolded chain: the weight gradients of
-// `rgb_features` need the `features` activations.  Reported FLOP counts always use the unfolded 593,408 MAC.
-// step:        0    1..4   5      6,7   8
-// layer:       L0   L1-4   L5     L6,7  [rgb_features o features | sigma]
-struct FwdFoldProg {
-  static constexpr int kSteps = 9;
-  static constexpr int kNLast = 144;                 // 128 rgb_features + sigma + 15 zero columns
-  __host__ __device__ static constexpr int layer(int s) { return s; }   // (s < 8; the last step is packed specially)
-  __host__ __device__ static constexpr int nk_h(int s) { return s == 0 ? 0 : 8; }
-  __host__ __device__ static constexpr int nk_x(int s) { return (s == 0 || s == 5) ? 2 : (s == 8 ? 1 : 0); }
-  __host__ __device__ static constexpr int N(int s) { return s == 8 ? kNLast : 256; }
-  static constexpr bool kHasBias = true;
   __host__ __device__ static constexpr int bias_a_chunk(int s) { return s <= 5 ? 6 : 2; }
 };
 
 // ---- backward (dgrad) steps --------------------------------------------------------------------------------
-// step b:      0               1                2 .. 8
-// computes:    dF = dG Wg^T    dZ7 = (dF Wf^T + dsigma Ws^T) * [h7>0]      dZ_{8-b} = (dZ_{9-b} W_{9-b}^T) * [h_{8-b}>0]
-// weights:     rgb_features    features         layer 7 .. layer 1        (rows < 256 of the Keras [in,out] kernel)
+// step b:      0                                                  1 .. 7
+// computes:    dZ7 = (dG W'^T + dsigma Ws^T) * [h7>0]             dZ_{7-b} = (dZ_{8-b} W_{8-b}^T) * [h_{7-b}>0]
+// weights:     W' = W_f W_g[:256] (K = 128 rgb_features columns)  layer 7 .. layer 1   (rows < 256 of the Keras kernel)
 struct BwdProg {
-  static constexpr int kSteps = 9;
-  __host__ __device__ static constexpr int layer(int b) { return b == 0 ? 10 : (b == 1 ? 9 : 9 - b); }
+  static constexpr int kSteps = 8;
+  __host__ __device__ static constexpr int layer(int b) { return 8 - b; }            // (b >= 1)
   __host__ __device__ static constexpr int nk_h(int b) { return b == 0 ? 4 : 8; }
   __host__ __device__ static constexpr int nk_x(int) { return 0; }
   __host__ __device__ static constexpr int N(int) { return 256; }
-  __host__ __device__ static constexpr int stage_bytes(int) { return kStageBytes; }
   static constexpr bool kHasBias = false;
-  __host__ __device__ static constexpr int bias_bytes(int) { return 0; }
   __host__ __device__ static constexpr int bias_a_chunk(int) { return 0; }
-  __host__ __device__ static constexpr int blob_off(int b) { return (b == 0 ? 0 : 4 + (b - 1) * 8) * kStageBytes; }
-  __host__ __device__ static constexpr int ld(int b) { return b == 0 ? 128 : 256; }       // fan_out of that kernel
 };
-constexpr int kBwdBlobBytes = BwdProg::blob_off(BwdProg::kSteps);
 
-// ---- cta_group::2 ("pair") weight layout ---------------------------------------------------------------------
+// ---- weight layout of the CTA-pair kernels -------------------------------------------------------------------
 // The chain kernels run as CTA pairs (cluster of 2): one M = 256 tcgen05.mma per K = 16 covers a 128-sample tile
 // in EACH CTA, and each CTA holds only HALF of the weight rows (N/2), so per SM the L2 -> smem weight traffic and
-// the B-operand smem reads are halved.  Stages are K = 64 wide (four MMAs per full/empty barrier round, which
-// keeps the single issuing thread ahead of the tensor pipe) and every (stage, CTA) piece is contiguous in the
-// blob, so a stage is ONE bulk copy per CTA:
+// the B-operand smem reads are halved.  Stages are K = 64 wide (four MMAs per full/empty barrier round) and every
+// (stage, CTA) piece is contiguous in the blob, so a stage is ONE bulk copy per CTA:
 //   step s: [stage 0: cta0 piece | cta1 piece][stage 1: ...] ... [bias stage: cta0 | cta1]
 //   piece = [k/8 chunks][N/2 rows][8]   (k = 64, or the 32-wide tail of the direction encoding, or 16 for the bias)
 constexpr int kPairK = 64;
@@ -124,16 +96,14 @@ struct PairLayout {
 };
 
 // ---- packed weight buffer ------------------------------------------------------------------------------------
-// [forward blob][dgrad blob][fp32 side table][forward pair blob][dgrad pair blob][folded inference pair blob].  The side table holds 16-byte
-// aligned copies (the Keras flat buffer is not aligned: the 1-wide sigma bias shifts everything after it):
-// bias[l] at l*256 (l = 0..11), sigma kernel [256] at 12*256, rgb kernel [128,3] at 13*256.
-constexpr int kBwdBlobOff = kFwdBlobBytes;
-constexpr int kAuxOff = kBwdBlobOff + kBwdBlobBytes;
+// [fp32 side table][forward blob][dgrad blob].  The side table holds 16-byte aligned copies (the Keras flat buffer
+// is not aligned: the 1-wide sigma bias shifts everything after it): bias[l] at l*256 (l = 0..11), sigma kernel
+// [256] at 12*256, rgb kernel [128,3] at 13*256.
+constexpr int kAuxOff = 0;
 constexpr int kAuxFloats = 12 * 256 + 256 + 512;
 constexpr int kFwdPairOff = kAuxOff + kAuxFloats * 4;
 constexpr int kBwdPairOff = kFwdPairOff + PairLayout<FwdProg>::kBytes;
-constexpr int kFoldPairOff = kBwdPairOff + PairLayout<BwdProg>::kBytes;
-constexpr int kPackedBytes = kFoldPairOff + PairLayout<FwdFoldProg>::kBytes;
+constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
 
 struct TcParams {
   int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
@@ -144,20 +114,21 @@ struct TcParams {
 constexpr int kRecXS = 0;                          // PE(xyz)      [8 chunks][128][8]   16 KB
 constexpr int kRecDS = 16384;                      // PE(dir)      [4 chunks][128][8]    8 KB (the next 8 KB are unused)
 constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
-constexpr int kRecF = kRecH0 + 8 * kHSBytes;       // features     64 KB
-constexpr int kRecG = kRecF + kHSBytes;            // rgb_features [16 chunks][128][8]  32 KB
+constexpr int kRecG = kRecH0 + 8 * kHSBytes;       // rgb_features [16 chunks][128][8]  32 KB
 constexpr int kRecMask = kRecG + 32768;            // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
 constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns h*128 + g*32 + (0..31) of row r;
                                                    //   bit i = column 2i, bit 16+i = column 2i+1 (bf16x2 packing order)
-constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 672 KB per 128 samples
+constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 608 KB per 128 samples
 // pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
 constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB
-constexpr int kDzF = 8 * kHSBytes;                 // d features   64 KB
-constexpr int kDzG = kDzF + kHSBytes;              // d rgb_features 32 KB
+constexpr int kDzG = 8 * kHSBytes;                 // d rgb_features 32 KB
 constexpr int kDzP = kDzG + 32768;                 // (d rgb_pre[3], d sigma_pre, 0...) [2 chunks][128][8]  4 KB
-constexpr int kDzBytes = kDzP + 4096;              // 612 KB per 128 samples
+constexpr int kDzBytes = kDzP + 4096;              // 548 KB per 128 samples
+// fp32 scratch at the head of the training workspace: X = h7^T dG [256 x 128], then sum(dG) [128]
+constexpr int kXFloats = 256 * 128 + 128;
+constexpr int kXBytes = ((kXFloats * 4 + 255) / 256) * 256;
 
-struct Chain2Smem {
+struct ChainSmem {
   uint8_t hs[2][kHSBytes];
   uint8_t xs[2][kXSBytes];
   uint8_t stage[kNumStages2][kStageBytes2];
@@ -166,15 +137,6 @@ struct Chain2Smem {
   uint32_t tmem_base;
   uint32_t items_issued;      // ordered mode: ring items whose MMAs have been issued (the two issuers take turns)
   uint32_t first_issued[2];   // unordered mode, per tile slot: GEMM steps whose first (accumulate = 0) MMA is issued
-};
-
-struct ChainSmem {
-  uint8_t hs[2][kHSBytes];
-  uint8_t xs[2][kXSBytes];
-  uint8_t stage[kNumStages][kStageBytes];
-  float part[kTileM][4];
-  uint64_t full[kNumStages], empty[kNumStages], a_ready[2], acc_ready[2], st_ready[2], st_done[2];
-  uint32_t tmem_base;
 };
 
 }  // namespace tcl

@@ -1,8 +1,8 @@
-// cta_group::2 variant of the chain-kernel roles (tc_roles.cuh): a CTA PAIR (cluster of 2 = one TPC) works on
+// Roles of the chain kernels: a CTA PAIR (cluster of 2 = one TPC) works on
 // four 128-sample tiles -- two per CTA, ping-pong as before -- and every GEMM step is ONE M=256 tcgen05.mma per
 // K=16 issued by the leader CTA: each CTA feeds its own A tile and HALF of the weight rows (N/2), so the
 // shared-memory traffic per SM (operand reads + TMA writes) and the L2->SM weight traffic are both halved, which
-// is what bounds the single-CTA kernel.  Weight stages are K = 64 wide (tc_layout.cuh PairLayout):
+// is what bounded the first, single-CTA version of these kernels.  Weight stages are K = 64 wide (tc_layout.cuh PairLayout):
 // the issuing thread spends ~150 cycles per stage on barriers, so four MMAs (512 tensor cycles) per stage keep it
 // ahead of the pipe where two (256 cycles) did not (benchmarks/micro/umma_rate.cu).
 //
@@ -20,7 +20,7 @@ namespace knerf {
 namespace tcl {
 using namespace tc;
 
-__device__ __forceinline__ uint32_t chain2_setup(Chain2Smem& sm, int tid, int warp, uint32_t cta) {
+__device__ __forceinline__ uint32_t chain2_setup(ChainSmem& sm, int tid, int warp, uint32_t cta) {
   if (tid == 0) {
     for (int i = 0; i < kNumStages2; ++i) {
       // leader: its own producer (arrive + tx bytes) and the peer's relay; peer: its producer only
@@ -50,7 +50,7 @@ __device__ __forceinline__ void chain2_teardown(uint32_t tmem, int warp) {
 
 // `blob` = the pair blob of this program (PairLayout<Prog>)
 template <class Prog>
-__device__ __forceinline__ void producer2_role(Chain2Smem& sm, const uint8_t* __restrict__ blob, uint32_t cta,
+__device__ __forceinline__ void producer2_role(ChainSmem& sm, const uint8_t* __restrict__ blob, uint32_t cta,
                                                int64_t n_quads, int64_t first, int64_t stride) {
   using PL = PairLayout<Prog>;
   uint32_t it = 0;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void producer2_role(Chain2Smem& sm, const uint8_t* __
 
 // peer CTA: forward "my piece of slot k has landed" to the leader's full barrier, in ring order
 template <class Prog>
-__device__ __forceinline__ void relay_role(Chain2Smem& sm, int64_t n_quads, int64_t first, int64_t stride) {
+__device__ __forceinline__ void relay_role(ChainSmem& sm, int64_t n_quads, int64_t first, int64_t stride) {
   using PL = PairLayout<Prog>;
   uint32_t it = 0;
   for (int64_t quad = first; quad < n_quads; quad += stride) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void relay_role(Chain2Smem& sm, int64_t n_quads, int6
 //    can differ in the last bit from run to run -- 16 % more throughput (1475 vs 1275 TFLOP/s).
 // Accumulation into the same TMEM tile from two threads is safe: the pipe executes MMAs one at a time.
 template <class Prog>
-__device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, uint32_t p, bool ordered, int64_t n_quads,
+__device__ __forceinline__ void mma2_role(ChainSmem& sm, uint32_t tmem, uint32_t p, bool ordered, int64_t n_quads,
                                           int64_t first, int64_t stride) {
   using PL = PairLayout<Prog>;
   uint32_t it = 0, a_par = 0;   // bit tl of a_par = parity of a_ready[tl]
@@ -192,7 +192,7 @@ __device__ __forceinline__ void mma2_role(Chain2Smem& sm, uint32_t tmem, uint32_
 
 // compute warps: "this warp's part of tile slot tl is written": publish to the async proxy, then ONE arrive per
 // warp on the leader's barrier (16 = 8 warps x 2 CTAs)
-__device__ __forceinline__ void a_ready_arrive2(Chain2Smem& sm, int tl, int lane) {
+__device__ __forceinline__ void a_ready_arrive2(ChainSmem& sm, int tl, int lane) {
   tc_fence_before();
   fence_async_smem();
   __syncwarp();

@@ -224,40 +224,40 @@ def test_umma_selftest_2cta(N, K):
 
 
 @pytest.mark.parametrize("R,S", [(37, 192), (300, 64), (1031, 192)])
-def test_tc_pair_kernels_match_single_cta(R, S):
-    """The chain kernels run as CTA pairs (cta_group::2 MMAs, K = 64 weight stages) by default; the single-CTA
-    kernels (K = 32 stages) are kept behind knerf_debug_tc_variant.  Same bf16 products, same fp32 accumulation
-    order per output element (K ascending, 16 per MMA) -> training forward output, saved records and the dgrad
-    record must be bit-identical, weight gradients equal up to the order of the fp32 atomics."""
+def test_tc_training_kernels_are_bit_reproducible(R, S):
+    """The chain kernels have TWO MMA-issuing threads (tc_roles2.cuh).  When training they hand over in ring order,
+    so the fp32 accumulation order is fixed: forward output, activation / ReLU' records and the dZ records are
+    bit-identical run after run; weight gradients differ only by the order of the fp32 atomics.  At inference the
+    issuers run free by default (last-bit differences allowed) and knerf_debug_tc_variant(3) restores the order."""
     from keras_nerf_b200 import _lib
     lib = _lib.load()
     _, m = _models(R)
     o, d, t, tgt = _rays(R, S, seed=11 + R)
-    res = {}
+    res = []
     try:
-        for variant in (1, 3):   # 3 = pairs with ordered MMA issue at inference too (training always is)
-            lib.knerf_debug_tc_variant(variant)
+        lib.knerf_debug_tc_variant(3)
+        for run in range(2):
             m._ws.zero_()
-            out = _fwd(m, m.fine, o, d, t, True)
             inf = _fwd(m, m.fine, o, d, t, False)
+            out = _fwd(m, m.fine, o, d, t, True)
             dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
             _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
                       2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
-            _fwd(m, m.fine, o, d, t, True)
             gbuf = torch.zeros_like(m.fine.params)
             _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
                       R, S, m._prec, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
             nbytes = int(lib.knerf_workspace_bytes(C.byref(m.cfg), R * S, m._prec, 1))
-            res[variant] = (out.clone(), inf.clone(), m._ws.view(torch.uint8)[:nbytes].clone(), gbuf.clone())
+            # skip the fp32 X scratch at the head of the workspace (atomics)
+            res.append((out.clone(), inf.clone(), m._ws.view(torch.uint8)[256 * 1024:nbytes].clone(), gbuf.clone()))
     finally:
         lib.knerf_debug_tc_variant(0)
-    a, b = res[1], res[3]
-    assert torch.equal(a[0], b[0])                                        # training forward
-    assert torch.equal(a[0], a[1])                                        # single CTA: saving records changes nothing
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])            # training / ordered inference forward
+    assert torch.equal(a[0], a[1])                                        # saving records does not change the output
     assert torch.equal(a[2], b[2])                                        # activation + ReLU' + dZ records
     scale = float(a[3].abs().max())
     assert scale > 0 and float((a[3] - b[3]).abs().max()) <= 1e-5 * scale
-    # The pair kernels' INFERENCE program folds `features` into `rgb_features` and takes sigma from the tensor core
-    # (tc_layout.cuh FwdFoldProg): the same function with one bf16 rounding less -- equal to bf16 tolerance
-    assert float((a[1][..., :3] - b[1][..., :3]).abs().max()) <= 5e-3
-    assert float((a[1][..., 3] - b[1][..., 3]).abs().max()) <= 1e-2 * max(1.0, float(a[1][..., 3].abs().max()))
+    free = _fwd(m, m.fine, o, d, t, False)                                # default: free-running issuers
+    # a different fp32 summation order can flip a bf16 rounding somewhere in the chain: bf16-level agreement
+    assert float((free[..., :3] - a[1][..., :3]).abs().max()) <= 2e-3
+    assert float((free[..., 3] - a[1][..., 3]).abs().max()) <= 1e-2 * max(1.0, float(a[1][..., 3].abs().max()))
