@@ -13,6 +13,8 @@
 //  3. tc_finish_kernel -- the weight gradients of `features` and of the first 256 rows of `rgb_features` from
 //     X = h7^T dG (tc_layout.cuh), a 256 x 256 x 128 problem once per call.
 #include "mlp_tc.cuh"
+
+#include <cstdlib>
 #include "tc_roles2.cuh"
 
 namespace knerf {
@@ -228,14 +230,17 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
 // weight gradients
 // =============================================================================================================
 constexpr int kWUnitBytes = 32768;     // 16 chunks x 128 samples x 16 B: 128 features (A) or 128 outputs (B)
-constexpr int kWSlots = 6;
+constexpr int kWSlots = 7;            // 7 x 32 KB in flight per CTA (224 KB of the 227 KB)
 constexpr int kWThreads = 192;         // warp 0 producer, warp 1 MMA, warps 2-5 flush
 constexpr int kNumTasks = 10;
 constexpr int kWMaxUnits = 6;
 
-struct WUnit { int src, off, bytes, bias_layer, bias_col0; };   // src 0 = forward record, 1 = dz record;
-                                                                // bias_layer >= 0: column sums of this dZ unit are db
-struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b; };
+// one ring slot: `bytes` from the forward (src 0) or dz (src 1) record at offset 0 and, optionally, `bytes2` from the
+// dz record at slot offset 8192 (two small operands share a slot); bias_layer >= 0: column sums of this dZ unit
+// are the bias gradient of that layer
+struct WUnit { int src, off, bytes, bias_layer, bias_col0, off2, bytes2; };
+// accumulator group: A = unit a (+ a_sub bytes), B = unit b (+ b_sub bytes)
+struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b, a_sub, b_sub; };
 struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; };
 // mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
 //      3: X = h7^T dG into the fp32 scratch (tc_finish_kernel turns it into dW_features and dW_rgb_features[:256])
@@ -268,7 +273,9 @@ static WTaskTable build_task_table() {
     t.n_groups = 2;
     t.g[0] = {0, 1, 0, 128, layer, row_base, 63, 0, 0, 0, 1};
     t.g[1] = {0, 2, 128, 128, layer, row_base, 63, 128, 0, 1, 1};
-    t.cost = 96;
+    t.cost = 76;    // costs = measured time per tile of a CTA working alone on the task (x 128 / the `big` tasks'):
+                    // 3,700 / 6,300 / 8,400 cycles -- the kernel is bound by its CTAs' per-tile time, so equal item
+                    // TIMES (not bytes) remove the tail
   };
   xpart(0, kDzZ0, 0);                                                        // layer 0
   for (int l = 1; l <= 7; ++l) big(l, kRecH0 + (l - 1) * kHSBytes, kDzZ0 + l * kHSBytes, 0);   // layers 1..7 (h part)
@@ -279,21 +286,21 @@ static WTaskTable build_task_table() {
      // Units in order of first use; groups ordered so that each unit is released as early as possible.
     WTask& t = T.t[n++];
     const int h7 = kRecH0 + 7 * kHSBytes;
-    t.n_units = 6;
-    t.u[0] = {0, h7, kWUnitBytes, -1, 0};                 // h7 features 0..127
-    t.u[1] = {1, kDzG, kWUnitBytes, 10, 0};               // dG (its column sums = db_rgb_features)
-    t.u[2] = {1, kDzP, 4096, -1, 0};                      // (d rgb_pre, d sigma_pre)
-    t.u[3] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0};   // h7 features 128..255
-    t.u[4] = {0, kRecDS, 8192, -1, 0};                    // PE(dir): 32 columns = 8 KB (27 valid accumulator rows)
-    t.u[5] = {0, kRecG, kWUnitBytes, -1, 0};              // rgb_features activations
+    t.n_units = 5;
+    t.u[0] = {0, h7, kWUnitBytes, -1, 0, 0, 0};                 // h7 features 0..127
+    t.u[1] = {1, kDzG, kWUnitBytes, 10, 0, 0, 0};               // dG (its column sums = db_rgb_features)
+    t.u[2] = {0, kRecDS, 8192, -1, 0, kDzP, 4096};              // PE(dir) (32 columns, 27 valid accumulator rows) and,
+                                                                // at +8192, the packed (d rgb_pre, d sigma_pre) operand
+    t.u[3] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0, 0, 0};   // h7 features 128..255
+    t.u[4] = {0, kRecG, kWUnitBytes, -1, 0, 0, 0};              // rgb_features activations
     t.n_groups = 6;
-    t.g[0] = {0, 1, 0, 128, -1, 0, 128, 0, 3, 0, 0};
-    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0};
-    t.g[2] = {3, 1, 128, 128, -1, 128, 128, 0, 3, 0, 0};
-    t.g[3] = {3, 2, 400, 16, 8, 128, 128, 0, 1, 1, 0};
-    t.g[4] = {4, 1, 256, 128, 10, 256, 27, 0, 0, 1, 1};
-    t.g[5] = {5, 2, 416, 16, 11, 0, 128, 0, 2, 1, 1};
-    t.cost = 128;
+    t.g[0] = {0, 1, 0, 128, -1, 0, 128, 0, 3, 0, 0, 0, 0};
+    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0, 0, 8192};
+    t.g[2] = {3, 1, 128, 128, -1, 128, 128, 0, 3, 0, 0, 0, 0};
+    t.g[3] = {3, 2, 400, 16, 8, 128, 128, 0, 1, 1, 0, 0, 8192};
+    t.g[4] = {2, 1, 256, 128, 10, 256, 27, 0, 0, 0, 1, 0, 0};
+    t.g[5] = {4, 2, 416, 16, 11, 0, 128, 0, 2, 1, 1, 0, 8192};
+    t.cost = 170;
   }
   return T;
 }
@@ -361,8 +368,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             const uint32_t slot = it % kWSlots, ph = (it / kWSlots) & 1;
             const uint8_t* src = (t.u[k].src == 0 ? rec + tile * kRecBytes : dz + tile * kDzBytes) + t.u[k].off;
             mbar_wait(&sm.empty[slot], ph ^ 1);
-            mbar_arrive_expect_tx(&sm.full[slot], t.u[k].bytes);
+            mbar_arrive_expect_tx(&sm.full[slot], t.u[k].bytes + t.u[k].bytes2);
             tma_load_1d(sm.slot[slot], src, t.u[k].bytes, &sm.full[slot]);
+            if (t.u[k].bytes2)
+              tma_load_1d(sm.slot[slot] + 8192, dz + tile * kDzBytes + t.u[k].off2, t.u[k].bytes2, &sm.full[slot]);
           }
         }
       }
@@ -390,7 +399,7 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             mbar_wait(&sm.full[sb], (ib / kWSlots) & 1);
             tc_fence_after();
             const uint32_t idesc = umma_idesc_bf16(128, g.N, 1, 1);
-            const uint32_t a_base = smem_u32(sm.slot[sa]), b_base = smem_u32(sm.slot[sb]);
+            const uint32_t a_base = smem_u32(sm.slot[sa]) + g.a_sub, b_base = smem_u32(sm.slot[sb]) + g.b_sub;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {   // K = 128 samples per tile, 16 per MMA; MN-major: LBO = 128 B, SBO = 2 KB
               const uint64_t da = umma_smem_desc(a_base + k * 256, 128, kChunkA);
@@ -580,7 +589,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   }
   if (g_bwd_parts & 2) {
     static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
-    // items ~ 2 x 148: 8 tasks of cost 128 and 2 of cost 96 -> 8 s + 2 * (3 s / 4) items for s slabs
+    // items ~ 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 170 -> 217 + 36 + 41 = 294 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
     const int grid = std::min(n_items, kNumSMs);
