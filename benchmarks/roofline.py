@@ -19,14 +19,14 @@ FLOP_FWD_INFER_EXECUTED = 2 * (593_408 - 256 * 256 + 288 * 16)
 FLOP_TRAIN_PER_SAMPLE = 3_489_024          # fwd + dgrad + wgrad
 FLOP_WGRAD_PER_SAMPLE = 1_186_816          # every weight once more
 FLOP_DGRAD_PER_SAMPLE = FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE - FLOP_WGRAD_PER_SAMPLE
-# bf16 mode, algorithmic HBM bytes per sample (records of 672 KB + 612 KB per 128 samples)
-BYTES_FWD_SAVE = 664 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
-BYTES_DGRAD = 8 * 32 + 612 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes the dZ record
-BYTES_WGRAD = 1388 * 1024 / 128                         # operand units of the 13 weight-gradient tasks
+# bf16 mode, algorithmic HBM bytes per sample (records of 608 KB + 548 KB per 128 samples)
+BYTES_FWD_SAVE = 600 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
+BYTES_DGRAD = 8 * 32 + 548 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes the dZ record
+BYTES_WGRAD = 1196 * 1024 / 128                         # operand units of the 10 weight-gradient tasks
 # measured DRAM traffic per sample from `ncu --set full` (profiles/r01_bf16_ncu_full.md, 393,216-sample launches)
-NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.002957 + 2.036844) * 1e9 / 393216,
-                          "tc_mlp_dgrad_kernel": (0.108136 + 1.866033) * 1e9 / 393216,
-                          "tc_wgrad_kernel": (4.355746 + 0.007782) * 1e9 / 393216}
+NCU_TRAFFIC_PER_SAMPLE = {"tc_mlp_fwd_kernel<train>": (0.002823 + 1.835313) * 1e9 / 393216,
+                          "tc_mlp_dgrad_kernel": (0.108100 + 1.666665) * 1e9 / 393216,
+                          "tc_wgrad_kernel": (3.750000 + 0.006960) * 1e9 / 393216}
 
 
 def _time_ms(fn, iters=5, warmup=2):
