@@ -38,41 +38,45 @@ __device__ __forceinline__ float fwd_weight(const float* __restrict__ params, co
   const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
   return row < fan_in ? params[P.w_off[L] + (int64_t)row * 256 + n] : 0.f;
 }
-// last forward step (tc_layout.cuh): reduction index k (h7, then the direction encoding), output column n; the
-// product W' = W_f W_g[:256] is formed here, in fp32
-__device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P, int k, int n) {
+// W' = W_f W_g[:256] [256,128] and its bias b_f W_g[:256] + b_g [128] in fp32 (tc_layout.cuh), one thread per element
+__global__ void __launch_bounds__(128) fold_kernel(const float* __restrict__ params, TcParams P, float* __restrict__ fold) {
   const float* Wf = params + P.w_off[9];    // features      [256, 256]
   const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
+  const int n = threadIdx.x, k = blockIdx.x;   // k = 256: the bias row
+  const float* row = k < 256 ? Wf + k * 256 : params + P.b_off[9];
+  float acc = k < 256 ? 0.f : params[P.b_off[10] + n];
+#pragma unroll 8
+  for (int j = 0; j < 256; ++j) acc = fmaf(row[j], Wg[j * 128 + n], acc);
+  fold[k * 128 + n] = acc;
+}
+// last forward step: reduction index k (h7, then the direction encoding), output column n
+__device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P,
+                                             const float* __restrict__ fold, int k, int n) {
   if (n < 128) {
-    if (k >= 256) return (k - 256 < 27) ? Wg[(int64_t)k * 128 + n] : 0.f;
-    float acc = 0.f;
-    for (int j = 0; j < 256; ++j) acc = fmaf(Wf[k * 256 + j], Wg[j * 128 + n], acc);
-    return acc;
+    if (k >= 256) return (k - 256 < 27) ? params[P.w_off[10] + (int64_t)k * 128 + n] : 0.f;
+    return fold[k * 128 + n];
   }
   return (n == 128 && k < 256) ? params[P.w_off[8] + k] : 0.f;   // sigma kernel [256, 1]
 }
-__device__ __forceinline__ float fold_bias(const float* __restrict__ params, const TcParams& P, int n) {
-  if (n < 128) {
-    float acc = params[P.b_off[10] + n];
-    for (int j = 0; j < 256; ++j) acc = fmaf(params[P.b_off[9] + j], params[P.w_off[10] + j * 128 + n], acc);
-    return acc;
-  }
-  return n == 128 ? params[P.b_off[8]] : 0.f;
+__device__ __forceinline__ float fold_bias(const float* __restrict__ params, const TcParams& P,
+                                           const float* __restrict__ fold, int n) {
+  return n < 128 ? fold[256 * 128 + n] : (n == 128 ? params[P.b_off[8]] : 0.f);
 }
 // B operand element of dgrad step b: output n = input feature of the layer (< 256), reduction index k = its output
 // feature.  b = 0 goes from d(rgb_features) straight to d(h7): W'[n][k]
-__device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P, int b, int k, int n) {
-  if (b == 0) return fold_weight(params, P, n, k);
+__device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P,
+                                            const float* __restrict__ fold, int b, int k, int n) {
+  if (b == 0) return fold[n * 128 + k];
   return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * 256 + k];
 }
 
 template <class Prog, bool FWD>
 __device__ __forceinline__ void pack_pair(const float* __restrict__ params, const TcParams& P,
-                                          uint8_t* __restrict__ blob, int gtid, int gsz) {
+                                          const float* __restrict__ fold, uint8_t* __restrict__ blob, int gtid, int gsz) {
   using PL = PairLayout<Prog>;
   auto weight = [&](int s, int k, int n) -> float {
-    if (!FWD) return bwd_weight(params, P, s, k, n);
-    return s == 8 ? fold_weight(params, P, k, n) : fwd_weight(params, P, s, k, n);
+    if (!FWD) return bwd_weight(params, P, fold, s, k, n);
+    return s == 8 ? fold_weight(params, P, fold, k, n) : fwd_weight(params, P, s, k, n);
   };
   for (int v = gtid; v < PL::kBytes / 16; v += gsz) {
     const int byte = v * 16;
@@ -95,7 +99,7 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
       const int cta = rem / pb, r2 = rem - cta * pb;
       const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
       if (cb == 1)
-        w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, cta * half + nl) : params[P.b_off[s] + cta * half + nl]);
+        w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, fold, cta * half + nl) : params[P.b_off[s] + cta * half + nl]);
     }
     *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -104,8 +108,9 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, TcParams P,
                                                    uint8_t* __restrict__ packed) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  pack_pair<FwdProg, true>(params, P, packed + kFwdPairOff, gtid, gsz);
-  pack_pair<BwdProg, false>(params, P, packed + kBwdPairOff, gtid, gsz);
+  const float* fold = reinterpret_cast<const float*>(packed + kFoldOff);   // written by fold_kernel
+  pack_pair<FwdProg, true>(params, P, fold, packed + kFwdPairOff, gtid, gsz);
+  pack_pair<BwdProg, false>(params, P, fold, packed + kBwdPairOff, gtid, gsz);
   float* aux = reinterpret_cast<float*>(packed + kAuxOff);
   for (int i = gtid; i < kAuxFloats; i += gsz) {
     const int blk = i >> 8, j = i & 255;
@@ -506,6 +511,8 @@ TcParams tc_make_params(const Model& m) {
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st) {
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_weights: packed must be 16-byte aligned");
+  fold_kernel<<<257, 128, 0, st>>>(params, tc_make_params(m), reinterpret_cast<float*>((uint8_t*)packed + kFoldOff));
+  KN_LAUNCH_CHECK();
   pack_kernel<<<kNumSMs * 2, 256, 0, st>>>(params, tc_make_params(m), (uint8_t*)packed);
   KN_LAUNCH_CHECK();
   return KNERF_OK;

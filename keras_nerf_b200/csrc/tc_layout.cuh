@@ -96,12 +96,14 @@ struct PairLayout {
 };
 
 // ---- packed weight buffer ------------------------------------------------------------------------------------
-// [fp32 side table][forward blob][dgrad blob].  The side table holds 16-byte aligned copies (the Keras flat buffer
+// [fp32 side table][fp32 folded kernel W' + bias][forward blob][dgrad blob].  The side table holds 16-byte aligned copies (the Keras flat buffer
 // is not aligned: the 1-wide sigma bias shifts everything after it): bias[l] at l*256 (l = 0..11), sigma kernel
 // [256] at 12*256, rgb kernel [128,3] at 13*256.
 constexpr int kAuxOff = 0;
 constexpr int kAuxFloats = 12 * 256 + 256 + 512;
-constexpr int kFwdPairOff = kAuxOff + kAuxFloats * 4;
+constexpr int kFoldOff = kAuxOff + kAuxFloats * 4;           // fp32 W' = W_f W_g[:256] [256,128], then its bias [128]
+constexpr int kFoldFloats = 256 * 128 + 128;
+constexpr int kFwdPairOff = kFoldOff + kFoldFloats * 4;
 constexpr int kBwdPairOff = kFwdPairOff + PairLayout<FwdProg>::kBytes;
 constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
 
