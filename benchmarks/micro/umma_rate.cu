@@ -10,7 +10,7 @@ using namespace knerf::tc;
 constexpr int kA = 128 * 256 * 2;      // one A tile [128 x 256] bf16
 constexpr int kStage = 256 * 32 * 2;   // one full-N weight stage (K = 32)
 
-template <bool TWO>
+template <bool TWO, bool MN = false>
 __global__ void __launch_bounds__(128) rate_kernel(int n_stages, int N, int commit_every, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_done, bar_full, bar_stage[8];
@@ -32,16 +32,17 @@ __global__ void __launch_bounds__(128) rate_kernel(int n_stages, int N, int comm
   const uint32_t tmem = tmem_base_s;
   long long t0 = 0, t1 = 0, t2 = 0;
   if (cta == 0 && tid == 0) {
-    const uint32_t idesc = umma_idesc_bf16(TWO ? 256 : 128, N, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(TWO ? 256 : 128, N, MN ? 1 : 0, MN ? 1 : 0);
     const uint32_t chunk_b = (uint32_t)(TWO ? N / 2 : N) * 16;
     t0 = clock64();
     for (int s = 0; s < n_stages; ++s) {
-      const uint32_t a_base = smem_u32(smem) + (s % 8) * 4 * 2048;
-      const uint32_t b_base = smem_u32(smem) + kA + (s % 4) * kStage;
+      const uint32_t a_base = smem_u32(smem) + (MN ? 0 : (s % 8) * 4 * 2048);
+      const uint32_t b_base = smem_u32(smem) + (MN ? 32768 : kA + (s % 4) * kStage);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const uint64_t da = umma_smem_desc(a_base + j * 2 * 2048, 2048, 128);
-        const uint64_t db = umma_smem_desc(b_base + j * 2 * chunk_b, chunk_b, 128);
+        // MN: the weight-gradient form (tc_ptx.cuh): K = rows of the blobs, LBO = 128 B (next 8 k), SBO = 2 KB (next 8 m|n)
+        const uint64_t da = MN ? umma_smem_desc(a_base + j * 256, 128, 2048) : umma_smem_desc(a_base + j * 2 * 2048, 2048, 128);
+        const uint64_t db = MN ? umma_smem_desc(b_base + j * 256, 128, 2048) : umma_smem_desc(b_base + j * 2 * chunk_b, chunk_b, 128);
         if (TWO) umma_bf16_2cta(tmem + (s & 256), da, db, idesc, s > 0);
         else umma_bf16(tmem + (s & 256), da, db, idesc, s > 0);
       }
@@ -65,13 +66,13 @@ __global__ void __launch_bounds__(128) rate_kernel(int n_stages, int N, int comm
   if (warp == 0) { if (TWO) tmem_dealloc_2cta<512>(tmem); else tmem_dealloc<512>(tmem); }
 }
 
-template <bool TWO>
+template <bool TWO, bool MN = false>
 void run(int grid, int n_stages, int N, int commit_every) {
   long long* d;
   cudaMalloc(&d, 148 * 2 * sizeof(long long));
   cudaMemset(d, 0, 148 * 2 * sizeof(long long));
   const size_t smem = kA + 4 * kStage;
-  cudaFuncSetAttribute(rate_kernel<TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(rate_kernel<TWO, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
@@ -81,7 +82,7 @@ void run(int grid, int n_stages, int N, int commit_every) {
     cfg.attrs = attr; cfg.numAttrs = 1;
   }
   for (int rep = 0; rep < 2; ++rep) {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, rate_kernel<TWO>, n_stages, N, commit_every, d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rate_kernel<TWO, MN>, n_stages, N, commit_every, d);
     if (e != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
   }
   long long h[296];
@@ -89,7 +90,7 @@ void run(int grid, int n_stages, int N, int commit_every) {
   double issue = 0, total = 0; int n = 0;
   for (int b = 0; b < grid; b += (TWO ? 2 : 1)) { issue += h[b * 2]; total += h[b * 2 + 1]; ++n; }
   printf("%s grid %3d N %3d stages %5d mode %2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)\n",
-         TWO ? "2-CTA M=256" : "1-CTA M=128", grid, N, n_stages, commit_every, issue / n / (2.0 * n_stages),
+         MN ? "1-CTA M=128 MN-major A and B" : TWO ? "2-CTA M=256" : "1-CTA M=128", grid, N, n_stages, commit_every, issue / n / (2.0 * n_stages),
          total / n / (2.0 * n_stages), N / 2);
   cudaFree(d);
 }
@@ -100,5 +101,9 @@ int main() {
     run<true>(148, 4096, 256, mode);
   }
   run<true>(148, 4096, 128, 7);
+  // weight-gradient form: both operands MN-major, N = 128 (floor 64) and N = 256
+  run<false>(148, 4096, 128, 0);
+  run<false, true>(148, 4096, 128, 0);
+  run<false, true>(148, 4096, 256, 0);
   return 0;
 }

@@ -261,3 +261,39 @@ def test_tc_training_kernels_are_bit_reproducible(R, S):
     # a different fp32 summation order can flip a bf16 rounding somewhere in the chain: bf16-level agreement
     assert float((free[..., :3] - a[1][..., :3]).abs().max()) <= 2e-3
     assert float((free[..., 3] - a[1][..., 3]).abs().max()) <= 1e-2 * max(1.0, float(a[1][..., 3].abs().max()))
+
+
+def test_tc_full_size_step_properties():
+    """BASELINE config[3] size (32,768 rays per step, 8.4 M samples, one chunk), where the oracle is out of reach:
+    size-independent properties -- composited pixels in [0, 1], compositing weights non-negative with sum <= 1,
+    depths inside [near, far]; two identical models take the same step (losses equal up to the order of the fp32
+    gradient atomics) and the loss goes down over three steps."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.data.synthetic import SyntheticScene
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    dev = torch.device("cuda")
+    R = 32768
+    scene = SyntheticScene(400, 64, n_views=100, device=dev)
+    img, rays = scene.ray_batch(3, R, offset=12345, seed=99)
+    logs = []
+    for rep in range(2):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision="bf16", device=dev)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=R // 256, image_width=256, ray_chunks=R,
+                  white_background=True)
+        u = torch.rand(R, 128, generator=torch.Generator().manual_seed(7)).to(dev)
+        logs.append([m.train_step((img, rays), u_fine=u) for _ in range(3)])
+        if rep == 1:
+            c, f = m.predict_and_render_images(rays, u_fine=u)
+        else:
+            del m
+            torch.cuda.empty_cache()
+    for a, b in zip(*logs):
+        assert b["fine_loss"] == pytest.approx(a["fine_loss"], rel=1e-4)
+        assert b["coarse_loss"] == pytest.approx(a["coarse_loss"], rel=1e-4)
+    assert logs[0][2]["fine_loss"] < logs[0][0]["fine_loss"]
+    for out, S in ((c, 64), (f, 192)):
+        im, w, dep = out["image"], out["weights"], out["depth"]
+        assert torch.isfinite(im).all() and float(im.min()) >= 0.0 and float(im.max()) <= 1.0
+        assert w.shape[-1] == S and float(w.min()) >= 0.0 and float(w.sum(-1).max()) <= 1.0 + 1e-4
+        assert float(dep.min()) >= 0.0 and float(dep.max()) <= 6.0 + 1e-3
