@@ -478,7 +478,10 @@ bool tc_path_compiled() { return true; }
 // outputs; training kernels always do).  0 / 2: default.
 static int g_tc_variant = 0;
 void tc_set_variant(int v) { g_tc_variant = v; }
-bool tc_ordered_issue() { return g_tc_variant == 3; }
+bool tc_ordered_issue() {
+  static const bool env = std::getenv("KNERF_TC_ORDERED") != nullptr;   // same switch from the environment
+  return g_tc_variant == 3 || env;
+}
 
 // diagnostic (-DKNERF_TC_TIMING builds only): copy and clear the forward kernel's per-CTA cycle counters
 int tc_debug_timing(unsigned long long* host_out, int n) {

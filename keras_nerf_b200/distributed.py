@@ -46,6 +46,13 @@ class RayShardedStrategy:
         lo = r * base + min(r, rem)
         return lo, lo + base + (1 if r < rem else 0)
 
+    def shard_bounds_of(self, rank: int, n: int):
+        """shard_bounds of another rank"""
+        w = self.num_replicas_in_sync
+        base, rem = divmod(n, w)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+
     def shard(self, x, dim=0):
         lo, hi = self.shard_bounds(x.shape[dim])
         return x.narrow(dim, lo, hi - lo)
@@ -69,14 +76,17 @@ class RayShardedStrategy:
         for net in (model.coarse, model.fine):
             dist.broadcast(net.params, src=src)
 
-    def gather_rows(self, x: torch.Tensor, n_total: int, dim=0):
-        """all ranks' shards (made by shard()/shard_bounds over n_total) -> full tensor on every rank"""
+    def gather_rows(self, x: torch.Tensor, n_total: int, dim=0, sizes=None):
+        """all ranks' shards -> full tensor on every rank.  Shards are those of shard()/shard_bounds over n_total, or
+        `sizes[r]` rows from rank r (e.g. whole ray chunks) when given."""
         w = self.num_replicas_in_sync
         if w == 1:
             return x
         x = x.movedim(dim, 0).contiguous()
-        base, rem = divmod(n_total, w)
-        sizes = [base + (1 if r < rem else 0) for r in range(w)]
+        if sizes is None:
+            base, rem = divmod(n_total, w)
+            sizes = [base + (1 if r < rem else 0) for r in range(w)]
+        assert sum(sizes) == n_total and x.shape[0] == sizes[self.rank]
         mx = max(sizes)
         pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         pad[:x.shape[0]] = x

@@ -303,6 +303,41 @@ class NeRF:
         fine = {'image': fi.view(B, H, W, 3), 'depth': fd.view(B, H, W), 'weights': fw.view(B, H, W, S)}
         return coarse, fine
 
+    def predict_and_render_images_sharded(self, rays, u_fine=None, seed=None, with_weights=False):
+        """Multi-GPU form of predict_and_render_images ("rendering just gathers pixels"): every rank
+        holds the same rays, renders a contiguous run of whole ray chunks and the pixels (rgb 12 B + depth 4 B per
+        ray; the [.., S] compositing weights only on request) are all-gathered, so every rank returns the full
+        images.  Same chunk seeds as the single-GPU call: the result does not depend on the number of ranks."""
+        st = self.strategy
+        if st is None or st.num_replicas_in_sync == 1:
+            return self.predict_and_render_images(rays, u_fine=u_fine, seed=seed)
+        o, d, t = self._flat_rays(rays)
+        n, S, rc = self.num_rays, self.n_coarse + self.n_fine, self.ray_chunks
+        u = self._u(u_fine, n)
+        lo, hi = st.shard_bounds(self.sequential_chunks)
+        m = (hi - lo) * rc
+        mk = lambda *s_: torch.empty(s_, dtype=torch.float32, device=self.device)  # noqa: E731
+        ci, cd, cw = mk(m, 3), mk(m), mk(m, self.n_coarse)
+        fi, fd, fw = mk(m, 3), mk(m), mk(m, S)
+        seed = next(_seed_counter) if seed is None else seed
+        for i in range(lo, hi):
+            s = slice(i * rc, (i + 1) * rc)
+            l = slice((i - lo) * rc, (i - lo + 1) * rc)
+            self._render_rays(o[s], d[s], t[s], None if u is None else u[s], seed + i * 0x9E3779B1,
+                              (ci[l], cd[l], cw[l]), (fi[l], fd[l], fw[l]))
+        sizes = [(b - a) * rc for a, b in (st.shard_bounds_of(r, self.sequential_chunks)
+                                           for r in range(st.num_replicas_in_sync))]
+        # one collective: [rgb_c, depth_c, rgb_f, depth_f] = 8 floats per ray
+        packed = torch.cat([ci, cd[:, None], fi, fd[:, None]], dim=1)
+        full = st.gather_rows(packed, n, 0, sizes=sizes)
+        B, H, W = self.batch_size, self.image_height, self.image_width
+        coarse = {'image': full[:, 0:3].reshape(B, H, W, 3), 'depth': full[:, 3].reshape(B, H, W)}
+        fine = {'image': full[:, 4:7].reshape(B, H, W, 3), 'depth': full[:, 7].reshape(B, H, W)}
+        if with_weights:
+            coarse['weights'] = st.gather_rows(cw, n, 0, sizes=sizes).reshape(B, H, W, self.n_coarse)
+            fine['weights'] = st.gather_rows(fw, n, 0, sizes=sizes).reshape(B, H, W, S)
+        return coarse, fine
+
     # ---- metrics (nerf.py:306-330) ------------------------------------------------------------
     def update_and_return_metrics(self, images, coarse_images, fine_images, coarse_loss, fine_loss):
         self.coarse_loss_tracker.update_state(float(coarse_loss))

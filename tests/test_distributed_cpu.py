@@ -44,6 +44,15 @@ def _worker(rank, world, port, q):
     got = st.gather_rows(mine.clone(), H, 0)
     assert torch.equal(got, full)
     assert st.mean_scalar(float(rank)) == pytest.approx(sum(range(world)) / world)
+    # sharded rendering gathers whole ray chunks: uneven chunk counts per rank (5 chunks of 4 rays over 2 ranks)
+    chunks, rc = 5, 4
+    bounds = [st.shard_bounds_of(r, chunks) for r in range(world)]
+    assert bounds[rank] == st.shard_bounds(chunks)
+    sizes = [(b - a) * rc for a, b in bounds]
+    px = torch.arange(chunks * rc * 8, dtype=torch.float32).reshape(chunks * rc, 8)
+    lo, hi = st.shard_bounds(chunks)
+    got = st.gather_rows(px[lo * rc:hi * rc].clone(), chunks * rc, 0, sizes=sizes)
+    assert torch.equal(got, px)
 
     class Net:  # broadcast of replicated weights
         def __init__(self, v):
