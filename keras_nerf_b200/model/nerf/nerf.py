@@ -109,7 +109,7 @@ class NeRF:
     def __init__(self, n_coarse: int = 64, n_fine: int = 128, pos_emb_xyz: int = 10, pos_emb_dir: int = 4,
                  n_layers: int = 8, dense_units: int = 256, skip_layer=4, model_path: str = None,
                  precision: str = "fp32", oob_mode: str = "zero", scan_mode: str = None, device=None,
-                 strategy=None, **kwargs):
+                 strategy=None, reproducible: bool = False, **kwargs):
         # keras_nerf/model/nerf/nerf.py:11-43
         self.model_path = model_path
         if self.model_path is None:
@@ -126,6 +126,13 @@ class NeRF:
         self.scan_mode = scan_mode or ("sequential" if precision in ("fp32", "float32") else "warp")
         self.device = torch.device(device) if device is not None else None
         self.strategy = strategy
+        # bf16 inference: the forward kernel's two MMA-issuing threads interleave freely by default (last-bit
+        # run-to-run differences, which the out-of-range gather quirk of the fine sampler can amplify in single
+        # pixels); reproducible=True makes them hand over in order like the training kernels (-14 % throughput).
+        # Process-wide switch of the library (knerf_debug_tc_variant).
+        self.reproducible = bool(reproducible)
+        if self.reproducible:
+            _lib.load().knerf_debug_tc_variant(3)
         self.coarse = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
                               name='coarse_nerf', device=device)
         self.fine = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
