@@ -23,15 +23,13 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&v)[P], int lane) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
       if (j >= P) {
+        // j >= P and k >= 2P: both bits lie in the lane part of e, so one predicate serves all P registers
         const int lj = j / P;
+        const bool take_min = (((lane * P) & k) == 0) == (((lane * P) & j) == 0);
 #pragma unroll
         for (int r = 0; r < P; ++r) {
-          const int e = lane * P + r;
-          const bool up = (e & k) == 0;
-          const bool lower = (e & j) == 0;
           const float o = __shfl_xor_sync(kFullMask, v[r], lj);
-          const float mn = fminf(v[r], o), mx = fmaxf(v[r], o);
-          v[r] = (lower == up) ? mn : mx;
+          v[r] = take_min ? fminf(v[r], o) : fmaxf(v[r], o);
         }
       } else {
 #pragma unroll
@@ -63,15 +61,26 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Nc = a.Nc, Nf = a.Nf;
   const int nc1 = (Nc + 1 + 3) & ~3;
-  float* cdf = smem + (size_t)wib * a.smem_per_warp;   // [Nc+1]
-  float* midp = cdf + nc1;                             // [Nc+1]: Nc-1 mid points + 2 out-of-range slots
-  float* tcs = midp + nc1;                             // [Nc]
-  float* fs = tcs + ((Nc + 3) & ~3);                   // [32*P] sorted fine samples
+  // cdf and the coarse depths are padded with +inf to CAP (a power of two > Nc + 1): every search below is a
+  // fixed-depth branchless upper bound, all of a lane's searches interleaved (independent LDS chains).
+  constexpr int CAP = 64 * NCB;
+  float* cdf = smem + (size_t)wib * a.smem_per_warp;   // [CAP]: Nc+1 entries + inf
+  float* tcs = cdf + CAP;                              // [CAP]: Nc entries + inf
+  float* midp = tcs + CAP;                             // [Nc+1]: Nc-1 mid points + 2 out-of-range slots
+  float* fs = midp + nc1;                              // [32*P] sorted fine samples (+inf beyond Nf)
   float* outs = fs + 32 * P;                           // [Nc+Nf]
-  const int64_t warp0 = (int64_t)blockIdx.x * kSampWarps + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kSampWarps;
+  for (int i = Nc + 1 + lane; i < CAP; i += 32) cdf[i] = CUDART_INF_F;
+  for (int i = Nc + lane; i < CAP; i += 32) tcs[i] = CUDART_INF_F;
+  // 4 consecutive draws per lane (one 16-byte load / one Philox block) when the row length allows it
+  const bool vec4 = (P >= 4) && (Nf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.u) & 15) == 0);
 
-  for (int64_t ray = warp0; ray < a.R; ray += nwarps) {
+  // The trip count depends on blockIdx only: the compiler can see that the body is not under divergent control
+  // flow, so the shuffles are bare SHFLs (a per-warp bound wrapped each one in WARPSYNC / collective barriers).
+  // Warps past the end redo the last ray and skip the stores.
+  for (int64_t base = (int64_t)blockIdx.x * kSampWarps; base < a.R; base += nwarps) {
+    const bool live = base + wib < a.R;
+    const int64_t ray = live ? base + wib : a.R - 1;
     // ---- pdf / cdf (utils.py:63-69) -----------------------------------------------------------
     float w[NCB], tc[NCB];
     float part = 0.f;
@@ -136,42 +145,70 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
     }
     __syncwarp();
     if (lane < 2) midp[Nc - 1 + lane] = (a.oob_mode == KNERF_OOB_CLAMP && Nc >= 2) ? midp[Nc - 2] : 0.f;
-    if (a.cdf_out != nullptr)
+    if (a.cdf_out != nullptr && live)
       for (int i = lane; i <= Nc; i += 32) a.cdf_out[ray * (Nc + 1) + i] = cdf[i];
     __syncwarp();
 
     // ---- inverse-CDF samples (utils.py:72-94) ---------------------------------------------------
-    float s[P];
+    float s[P], uu[P];
+    int fidx[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) fidx[r] = vec4 ? ((r >> 2) * 128 + lane * 4 + (r & 3)) : (r * 32 + lane);
+    if (vec4) {
+#pragma unroll
+      for (int q = 0; q < (P >= 4 ? P / 4 : 1); ++q) {
+        const int f0 = q * 128 + lane * 4;
+        float4 v4 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        if (f0 < Nf) {
+          const int64_t e0 = ray * Nf + f0;                 // e0 % 4 == 0
+          if (a.u != nullptr) {
+            v4 = __ldcs(reinterpret_cast<const float4*>(a.u + e0));
+          } else {
+            uint32_t rr[4];
+            philox4x32(a.seed, (uint64_t)e0 >> 2, rr);     // == philox_uniform(seed, e0 + 0..3)
+            v4 = make_float4(u01(rr[0]), u01(rr[1]), u01(rr[2]), u01(rr[3]));
+          }
+        }
+        if (4 * q + 3 < P) { uu[4 * q] = v4.x; uu[4 * q + 1] = v4.y; uu[4 * q + 2] = v4.z; uu[4 * q + 3] = v4.w; }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < P; ++r) {
+        const int64_t e = ray * Nf + fidx[r];
+        uu[r] = CUDART_NAN_F;
+        if (fidx[r] < Nf) uu[r] = (a.u != nullptr) ? ld_stream(a.u + e) : philox_uniform(a.seed, (uint64_t)e);
+      }
+    }
+    int idx[P];                                       // searchsorted(cdf, u, side='right') = #{cdf_j <= u}
+#pragma unroll
+    for (int r = 0; r < P; ++r) idx[r] = 0;
+#pragma unroll
+    for (int step = CAP / 2; step >= 1; step >>= 1) {
+#pragma unroll
+      for (int r = 0; r < P; ++r) idx[r] += (cdf[idx[r] + step - 1] <= uu[r]) ? step : 0;
+    }
     int oob = 0;
 #pragma unroll
     for (int r = 0; r < P; ++r) {
-      const int f = r * 32 + lane;
       s[r] = CUDART_INF_F;
-      if (f < Nf) {
-        const int64_t e = ray * Nf + f;
-        const float uu = (a.u != nullptr) ? ld_stream(a.u + e) : philox_uniform(a.seed, (uint64_t)e);
-        int lo = 0, hi = Nc + 1;                      // searchsorted(cdf, u, side='right')
-        while (lo < hi) {
-          const int m = (lo + hi) >> 1;
-          if (cdf[m] <= uu) lo = m + 1; else hi = m;
-        }
-        const int idx = lo;
-        const int below = max(idx - 1, 0);            // utils.py:78
-        const int above = min(idx, Nc);               // utils.py:79 (cdf.shape[-1]-1 == Nc)
+      if (fidx[r] < Nf) {
+        const int below = max(idx[r] - 1, 0);         // utils.py:78
+        const int above = min(idx[r], Nc);            // utils.py:79 (cdf.shape[-1]-1 == Nc)
         const float c0 = cdf[below], c1 = cdf[above];
         const float m0 = midp[below], m1 = midp[above];
         if (above >= Nc - 1) oob = 1;
         float den = __fsub_rn(c1, c0);
         if (den < 1e-5f) den = 1.0f;                  // utils.py:91
-        const float tt = __fdiv_rn(__fsub_rn(uu, c0), den);
+        const float tt = __fdiv_rn(__fsub_rn(uu[r], c0), den);
         s[r] = __fadd_rn(m0, __fmul_rn(tt, __fsub_rn(m1, m0)));   // utils.py:93-94
-        if (a.samples != nullptr) a.samples[e] = s[r];
-        if (a.indices != nullptr) a.indices[e] = idx;
+        const int64_t e = ray * Nf + fidx[r];
+        if (a.samples != nullptr && live) a.samples[e] = s[r];
+        if (a.indices != nullptr && live) a.indices[e] = idx[r];
       }
     }
     if (a.oob_mode == KNERF_OOB_COUNT && a.oob_count != nullptr) {
       const unsigned any = __ballot_sync(kFullMask, oob);
-      if (lane == 0 && any) atomicAdd(a.oob_count, 1);   // rays (not samples) with an out-of-range gather
+      if (lane == 0 && any && live) atomicAdd(a.oob_count, 1);   // rays (not samples) with an out-of-range gather
     }
     if (a.t_sorted == nullptr) { __syncwarp(); continue; }
 
@@ -180,28 +217,40 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
 #pragma unroll
     for (int r = 0; r < P; ++r) fs[lane * P + r] = s[r];
     __syncwarp();
+    {
+      int cnt[P];                                     // coarse entries <= v (a fine sample goes after equal coarse ones)
 #pragma unroll
-    for (int r = 0; r < P; ++r) {
-      const int e = lane * P + r;
-      if (e < Nf) {
-        const float v = s[r];
-        int lo = 0, hi = Nc;                          // coarse entries <= v
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (tcs[m] <= v) lo = m + 1; else hi = m; }
-        outs[e + lo] = v;
+      for (int r = 0; r < P; ++r) cnt[r] = 0;
+#pragma unroll
+      for (int step = CAP / 2; step >= 1; step >>= 1) {
+#pragma unroll
+        for (int r = 0; r < P; ++r) cnt[r] += (tcs[cnt[r] + step - 1] <= s[r]) ? step : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < P; ++r) {
+        const int e = lane * P + r;
+        if (e < Nf) outs[e + cnt[r]] = s[r];
       }
     }
+    {
+      int cnt[NCB];                                   // fine entries < v
 #pragma unroll
-    for (int j = 0; j < NCB; ++j) {
-      const int i = j * 32 + lane;
-      if (i < Nc) {
-        const float v = tc[j];
-        int lo = 0, hi = Nf;                          // fine entries < v
-        while (lo < hi) { const int m = (lo + hi) >> 1; if (fs[m] < v) lo = m + 1; else hi = m; }
-        outs[i + lo] = v;
+      for (int j = 0; j < NCB; ++j) cnt[j] = 0;
+#pragma unroll
+      for (int step = 16 * P; step >= 1; step >>= 1) {
+#pragma unroll
+        for (int j = 0; j < NCB; ++j) cnt[j] += (fs[cnt[j] + step - 1] < tc[j]) ? step : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < NCB; ++j) {
+        const int i = j * 32 + lane;
+        cnt[j] += (fs[cnt[j]] < tc[j]) ? 1 : 0;       // the search above tops out at 32P-1; all 32P may be smaller
+        if (i < Nc) outs[i + cnt[j]] = tc[j];
       }
     }
     __syncwarp();
-    for (int i = lane; i < Nc + Nf; i += 32) a.t_sorted[ray * (Nc + Nf) + i] = outs[i];
+    if (live)
+      for (int i = lane; i < Nc + Nf; i += 32) a.t_sorted[ray * (Nc + Nf) + i] = outs[i];
     __syncwarp();
   }
 }
@@ -246,7 +295,8 @@ extern "C" int knerf_sample_fine(const float* t_coarse, const float* mid_points,
   SampleArgs a{t_coarse, mid_points, weights, u, seed, cdf_in, R, Nc, Nf, oob_mode, sequential,
                t_sorted, samples, indices, cdf_out, oob_count, 0};
   const int nc1 = (Nc + 1 + 3) & ~3;
-  a.smem_per_warp = 2 * nc1 + ((Nc + 3) & ~3) + 32 * P + ((Nc + Nf + 3) & ~3);
+  const int cap = 64 * (ncb <= 2 ? ncb : (ncb <= 4 ? 4 : 8));
+  a.smem_per_warp = 2 * cap + nc1 + 32 * P + ((Nc + Nf + 3) & ~3);
   const size_t smem = (size_t)a.smem_per_warp * kSampWarps * sizeof(float);
   const int grid = (int)std::min<int64_t>(cdiv(R, kSampWarps), (int64_t)kNumSMs * 12);
   cudaStream_t st = (cudaStream_t)stream;

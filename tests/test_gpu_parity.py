@@ -284,6 +284,28 @@ def test_sampler_sorted_merge(Nc, Nf):
     assert maxerr(samples, so) <= 1e-6
 
 
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (64, 256), (32, 64), (16, 40)])
+def test_sampler_builtin_rng_is_the_knerf_uniform_stream(Nc, Nf):
+    """u=NULL draws sample e of the ray batch from Philox index e: same rows as passing knerf_uniform()'s output
+    (covers the 4-draws-per-lane path and the scalar one)."""
+    gpu()
+    from keras_nerf_b200 import _lib
+    dev = torch.device("cuda")
+    R = 77
+    g = torch.Generator().manual_seed(Nc + Nf)
+    tc_d = torch.sort(torch.rand(R, Nc, generator=g) * 4 + 2, dim=-1).values.to(dev).contiguous()
+    w_d = (torch.rand(R, Nc, generator=g) ** 4).to(dev)
+    u_d = torch.empty(R, Nf, device=dev)
+    _lib.call("knerf_uniform", _lib.ptr(u_d), R * Nf, 99, 0, _lib.stream())
+    outs = []
+    for u_ptr in (None, _lib.ptr(u_d)):
+        ts, sm = torch.empty(R, Nc + Nf, device=dev), torch.empty(R, Nf, device=dev)
+        _lib.call("knerf_sample_fine", _lib.ptr(tc_d), None, _lib.ptr(w_d), u_ptr, 99, None, R, Nc, Nf, 0,
+                  _lib.ptr(ts), _lib.ptr(sm), None, None, None, _lib.stream())
+        outs.append((ts, sm))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_sampler_builtin_rng_statistics():
     gpu()
     from keras_nerf_b200 import _lib
