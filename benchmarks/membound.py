@@ -74,6 +74,13 @@ def main():
     ms = time_ms(lambda: _lib.call("knerf_generate_rays", c2w.ctypes.data, H, W, 1111.0, 2.0, 6.0, 64, None, 7,
                                    _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), _lib.stream()))
     report("generate_rays 800x800 N=64 (Philox)", 24 + 4 * 64, ms, rays=H * W)
+    for (ih, iw), (oh, ow) in (((800, 800), (400, 400)), ((800, 800), (800, 800)), ((4096, 4096), (2048, 2048))):
+        src = torch.randint(0, 256, (ih, iw, 4), dtype=torch.uint8, device=dev)
+        dst = torch.empty(oh, ow, 4, device=dev)
+        ms = time_ms(lambda: _lib.call("knerf_image_prepare", _lib.ptr(src, torch.uint8), ih, iw, oh, ow, 1,
+                                       _lib.ptr(dst), _lib.stream()))
+        report(f"image_prepare {ih}x{iw} -> {oh}x{ow} (per output pixel)", 16 + 4.0 * ih * iw / (oh * ow), ms,
+               rays=oh * ow)
     n = 2 * 595844
     pbuf, gbuf, mbuf, vbuf = (torch.zeros(n, device=dev) for _ in range(4))
     ms = time_ms(lambda: _lib.call("knerf_adam_step", _lib.ptr(pbuf), _lib.ptr(gbuf), _lib.ptr(mbuf), _lib.ptr(vbuf), n, 1e-3,

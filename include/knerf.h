@@ -189,6 +189,15 @@ int knerf_adam_step(float* params, float* grads, float* m, float* v, int64_t n, 
 /* sum_c,rays (a-b)^2 / n  -> out[0] (device float); used for test_step losses / PSNR (nerf.py:306-330) */
 int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* ---- f3  ImageLoader.__call__ after the PNG decode  (keras_nerf/data/image.py:17-35) --------------------
+ * rgba: [in_h, in_w, 4] uint8 (DEVICE; what tf.io.decode_image(channels=4) yields).  Fuses
+ * convert_image_dtype (x * 1/255), tf.image.resize(bilinear, antialias=True) (ScaleAndTranslate, triangle
+ * kernel, rows then columns, fp32 sums in span order), the alpha composite on a white (1) / black (0)
+ * background, the alpha concat and the [0,1] clip.  out: [out_h, out_w, 4] float32.  Note that the reference
+ * passes (image_width, image_height) as tf.image.resize's (height, width) (image.py:22-23).                */
+int knerf_image_prepare(const uint8_t* rgba, int in_h, int in_w, int out_h, int out_w, int white_background,
+                        float* out, void* stream);
+
 /* Diagnostic: one tcgen05 tile, D[128,N] (fp32, row-major) = A[128,K] * B[N,K]^T from bf16 operand blobs in
  * the library's chunk-major layout ([K/8][rows][8] for mode 0 = K-major; [rows/8][K][8] for mode 1 =
  * MN-major, the weight-gradient form).  Pins the UMMA descriptor encoding in tests/test_gpu_tc.py.        */

@@ -55,3 +55,36 @@ class SyntheticScene:
         sh = (1, n_rays // 256, 256)
         f = lambda x: x.reshape(total, -1)[sl].reshape(sh + (x.shape[-1],)).contiguous()  # noqa: E731
         return f(img), (f(o), f(d), f(t))
+
+
+def write_nerf_synthetic_like(data_dir: str, image_wh: int = 64, n_train: int = 8, n_val: int = 2, n_test: int = 2,
+                              phi: float = -30.0, radius: float = 4.0) -> str:
+    """A nerf_synthetic-shaped directory (transforms_{train,val,test}.json + RGBA PNG frames, the layout
+    loader.py:41-76 reads) of the analytic sphere scene, for tests and examples.  Host-only (torch CPU + Pillow)."""
+    import json
+    import os
+
+    import numpy as np
+    from PIL import Image
+
+    focal = get_focal_from_fov(LEGO_FOV, image_wh)
+    ys, xs = torch.meshgrid(torch.arange(image_wh, dtype=torch.float32), torch.arange(image_wh, dtype=torch.float32),
+                            indexing="ij")
+    cam = torch.stack([(xs - image_wh * 0.5) / focal, -(ys - image_wh * 0.5) / focal, -torch.ones_like(xs)], dim=-1)
+    k = 0
+    for subset, n in (("train", n_train), ("val", n_val), ("test", n_test)):
+        os.makedirs(os.path.join(data_dir, subset), exist_ok=True)
+        frames = []
+        for i in range(n):
+            c2w = torch.from_numpy(np.asarray(pose_spherical(360.0 * k / (n_train + n_val + n_test), phi, radius),
+                                              dtype=np.float32))
+            k += 1
+            d = torch.nn.functional.normalize(cam @ c2w[:3, :3].T, dim=-1)
+            o = c2w[:3, 3].expand_as(d)
+            rgba = analytic_rgba(o, d, white_background=False)      # straight colour * alpha on black == premultiplied
+            png = (rgba.numpy() * 255.0 + 0.5).astype(np.uint8)
+            Image.fromarray(png, mode="RGBA").save(os.path.join(data_dir, subset, f"r_{i}.png"))
+            frames.append({"file_path": f"./{subset}/r_{i}", "rotation": 0.0, "transform_matrix": c2w.tolist()})
+        with open(os.path.join(data_dir, f"transforms_{subset}.json"), "w") as f:
+            json.dump({"camera_angle_x": LEGO_FOV, "frames": frames}, f)
+    return data_dir

@@ -153,6 +153,13 @@ class NeRF:
         self.coarse.save_weights(os.path.join(path, 'coarse.h5'))
         self.fine.save_weights(os.path.join(path, 'fine.h5'))
 
+    @staticmethod
+    def has_checkpoint(path) -> bool:
+        """the existence check of the scripts (train_single.py:91-92, inference.py:51-54): `coarse.h5` + `fine.h5`,
+        which this package stores as `.npz` archives with the Keras variable names"""
+        return all(any(os.path.exists(os.path.join(path, n + ext)) for ext in ('.npz', '.h5'))
+                   for n in ('coarse', 'fine'))
+
     def load_model(self, path):
         with open(os.path.join(path, 'model_config.json'), 'r') as f:
             mc = json.load(f)
