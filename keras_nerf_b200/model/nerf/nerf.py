@@ -468,4 +468,5 @@ class NeRF:
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
                     cb.on_epoch_end(epoch, logs)
+        self.history = history
         return history
