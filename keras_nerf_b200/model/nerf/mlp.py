@@ -123,7 +123,9 @@ class NeRFMLP:
                 print_fn(f"  {name:<14} Dense  ({fi} -> {fo})  params {fi * fo + fo}")
         print_fn(f"Total params: {self.count_params()}")
 
-    # ---- weight I/O (Keras [in,out] layout; .npz container -- HDF5 compat is SURVEY row f2) ------
+    # ---- weight I/O (Keras [in,out] layout) ----------------------------------------------------
+    # `*.h5` paths are Keras' legacy HDF5 weight files (nerf.py:63-64,134-136) through utils/hdf5.py (h5py is not
+    # a dependency); any other path is an .npz archive with the same `<layer>/<kernel:0|bias:0>` names.
     def get_weights(self):
         return [v.detach().cpu().numpy().copy() for v in self.trainable_variables]
 
@@ -133,13 +135,21 @@ class NeRFMLP:
                 v.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)).reshape(v.shape))
 
     def save_weights(self, path):
-        path = path[:-3] + ".npz" if path.endswith(".h5") else path
-        np.savez(path, **{f"{n}/{k}": w for n, (k, w) in
-                          zip(np.repeat(self.layer_names, 2), zip(["kernel:0", "bias:0"] * len(self.layer_names),
-                                                                 self.get_weights()))})
+        w = self.get_weights()
+        if path.endswith(".h5") or path.endswith(".hdf5"):
+            from ...utils.hdf5 import save_keras_weights
+            save_keras_weights(path, self.name, list(self.layer_names), [w[i:i + 2] for i in range(0, len(w), 2)])
+            return
+        np.savez(path, **{f"{n}/{k}": a for n, (k, a) in
+                          zip(np.repeat(self.layer_names, 2), zip(["kernel:0", "bias:0"] * len(self.layer_names), w))})
 
     def load_weights(self, path):
-        path = path[:-3] + ".npz" if path.endswith(".h5") else path
+        if (path.endswith(".h5") or path.endswith(".hdf5")) and os.path.exists(path):
+            from ...utils.hdf5 import load_keras_weights
+            self.set_weights(load_keras_weights(path, list(self.layer_names)))
+            return
+        if path.endswith(".h5"):
+            path = path[:-3] + ".npz"                          # checkpoints written before HDF5 support
         if not os.path.exists(path) and os.path.exists(path + ".npz"):
             path = path + ".npz"
         z = np.load(path)
