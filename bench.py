@@ -197,8 +197,10 @@ def main():
         strategy.broadcast_parameters(model)
     scene = SyntheticScene(IMG_WH, N_COARSE, n_views=100, device=dev)
     nb = 4
-    batches = [scene.ray_batch(rank * 25 + k, RAYS_PER_GPU, offset=k * 31337 + rank * 977, seed=1000 + rank * nb + k)
-               for k in range(nb)]
+    # 128 x 256 crops (32,768 rays) of four views per rank, placed so that each mixes sphere and background
+    crop_h, crop_w = RAYS_PER_GPU // 256, 256
+    batches = [scene.ray_crop(rank * 25 + 6 * k, crop_h, crop_w, y0=(40, 230, 110, 180)[k % 4] + 3 * rank,
+                              x0=(20, 124, 72, 60)[k % 4] + 5 * rank, seed=1000 + rank * nb + k) for k in range(nb)]
     host = [(img.cpu().pin_memory(), tuple(r.cpu().pin_memory() for r in rays)) for img, rays in batches]
     h2d = sum(x.numel() * 4 for x in (host[0][0],) + host[0][1])
 

@@ -189,6 +189,15 @@ int knerf_adam_step(float* params, float* grads, float* m, float* v, int64_t n, 
 /* sum_c,rays (a-b)^2 / n  -> out[0] (device float); used for test_step losses / PSNR (nerf.py:306-330) */
 int knerf_mse(const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* ---- a18 / f1  per-image metrics of NeRF.update_and_return_metrics  (keras_nerf/model/nerf/nerf.py:306-330) ---
+ * a, b: [B,H,W,C] float32.  mse[B] = mean (a-b)^2 per image (tf.image.psnr(max_val=1) = -10 log10 of it);
+ * ssim[B] = tf.image.ssim(a, b, max_val) with its defaults (11x11 gaussian window, sigma 1.5, k1 .01, k2 .03,
+ * VALID positions, mean over positions and channels).  Either output may be NULL.  H, W >= 11.  `workspace`:
+ * knerf_image_metrics_workspace_floats(B,H,W,C) floats of device scratch.  Bit-reproducible (fixed-order sums). */
+int64_t knerf_image_metrics_workspace_floats(int B, int H, int W, int C);
+int knerf_image_metrics(const float* a, const float* b, int B, int H, int W, int C, float max_val, float* mse,
+                        float* ssim, float* workspace, int64_t workspace_floats, void* stream);
+
 /* ---- f3  ImageLoader.__call__ after the PNG decode  (keras_nerf/data/image.py:17-35) --------------------
  * rgba: [in_h, in_w, 4] uint8 (DEVICE; what tf.io.decode_image(channels=4) yields).  Fuses
  * convert_image_dtype (x * 1/255), tf.image.resize(bilinear, antialias=True) (ScaleAndTranslate, triangle

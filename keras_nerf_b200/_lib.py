@@ -62,6 +62,8 @@ SIGNATURES = {
     "knerf_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _L, _I, _P]),
     "knerf_mse": (_I, [_P, _P, _L, _P, _P]),
     "knerf_image_prepare": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "knerf_image_metrics_workspace_floats": (_L, [_I, _I, _I, _I]),
+    "knerf_image_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _L, _P]),
     "knerf_debug_backward_parts": (_I, [_I]),
     "knerf_debug_tc_timing": (_I, [_P, _I]),
     "knerf_debug_tc_variant": (_I, [_I]),

@@ -19,7 +19,7 @@ LEGO_FOV = 0.6911112070083618
 ALBEDO = 0.6
 
 
-def analytic_rgba(o: torch.Tensor, d: torch.Tensor, white_background: bool = True) -> torch.Tensor:
+def analytic_rgba(o: torch.Tensor, d: torch.Tensor, white_background: bool = True, albedo: float = None) -> torch.Tensor:
     """o, d [...,3] -> RGBA [...,4] of a unit sphere at the origin, composited like image.py:25-33."""
     b = (o * d).sum(-1)
     c = (o * o).sum(-1) - 1.0
@@ -27,7 +27,7 @@ def analytic_rgba(o: torch.Tensor, d: torch.Tensor, white_background: bool = Tru
     hit = disc > 0
     t = -b - torch.sqrt(disc.clamp_min(0))
     n = torch.nn.functional.normalize(o + d * t[..., None], dim=-1)
-    rgb = (ALBEDO * 0.5 * (n + 1.0)).clamp(0, 1)
+    rgb = ((ALBEDO if albedo is None else albedo) * 0.5 * (n + 1.0)).clamp(0, 1)
     alpha = hit.to(o.dtype)[..., None]
     bg = torch.ones_like(rgb) if white_background else torch.zeros_like(rgb)
     img = alpha * rgb + (1.0 - alpha) * bg
@@ -49,6 +49,14 @@ class SyntheticScene:
         """(image[H,W,4], (o[H,W,3], d[H,W,3], t[H,W,Nc])) of view k with fresh stratified jitter."""
         o, d, t = self.gen(self.pose(k), seed=seed)
         return analytic_rgba(o, d, self.white), (o, d, t)
+
+    def ray_crop(self, k: int, h: int, w: int, y0: int, x0: int, seed=None):
+        """an h x w image crop of view k at (y0, x0), shaped [1, h, w, .] for NeRF.compile(image_height=h,
+        image_width=w): a genuine sub-image (SSIM stays meaningful) that mixes object and background"""
+        img, (o, d, t) = self.view(k, seed=seed)
+        y0, x0 = max(0, min(y0, self.wh - h)), max(0, min(x0, self.wh - w))
+        f = lambda x: x[y0:y0 + h, x0:x0 + w][None].contiguous()  # noqa: E731
+        return f(img), (f(o), f(d), f(t))
 
     def ray_batch(self, k: int, n_rays: int, offset: int = 0, seed=None):
         """a contiguous window of n_rays rays of view k, shaped [1, n_rays/256, 256, .] for NeRF.compile"""

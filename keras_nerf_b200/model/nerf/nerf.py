@@ -77,29 +77,25 @@ class Mean:
     reset_states = reset_state
 
 
-def _psnr(a, b):
-    """tf.image.psnr(a, b, max_val=1.0) per image (nerf.py:309,311)."""
-    m = ((a - b) ** 2).reshape(a.shape[0], -1).mean(dim=1)
-    return -10.0 * torch.log10(m)
-
-
-def _ssim(a, b, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03):
-    """tf.image.ssim(a, b, max_val=1.0) per image (nerf.py:310,312); host-side torch glue, off the hot path."""
-    if min(a.shape[1], a.shape[2]) < filter_size:
-        return torch.full((a.shape[0],), float("nan"), device=a.device)
-    a, b = a.permute(0, 3, 1, 2), b.permute(0, 3, 1, 2)
-    ch = a.shape[1]
-    g = torch.arange(filter_size, dtype=torch.float32, device=a.device) - (filter_size - 1) / 2.0
-    g = torch.exp(-(g * g) / (2.0 * filter_sigma * filter_sigma))
-    g = g / g.sum()
-    k = (g[:, None] * g[None, :]).expand(ch, 1, filter_size, filter_size).contiguous()
-    conv = lambda x: torch.nn.functional.conv2d(x, k, groups=ch)  # noqa: E731
-    c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
-    mu_a, mu_b = conv(a), conv(b)
-    s_aa, s_bb, s_ab = conv(a * a) - mu_a * mu_a, conv(b * b) - mu_b * mu_b, conv(a * b) - mu_a * mu_b
-    lum = (2 * mu_a * mu_b + c1) / (mu_a * mu_a + mu_b * mu_b + c1)
-    cs = (2 * s_ab + c2) / (s_aa + s_bb + c2)
-    return (lum * cs).mean(dim=(1, 2, 3))
+def image_metrics(a: torch.Tensor, b: torch.Tensor, max_val: float = 1.0):
+    """(tf.image.psnr(a, b, max_val), tf.image.ssim(a, b, max_val)) per image (nerf.py:309-312) as one [2, B] CUDA
+    tensor, from `knerf_image_metrics` (per-image MSE and 11x11-gaussian-window SSIM in one pass).
+    Images smaller than the SSIM window give NaN SSIM (TF raises there)."""
+    a, b = a.contiguous(), b.contiguous()
+    B, H, W, Cn = a.shape
+    out = torch.full((2, B), float("nan"), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        if H >= 11 and W >= 11:
+            n = _lib.load().knerf_image_metrics_workspace_floats(B, H, W, Cn)
+            ws = torch.empty(n, dtype=torch.float32, device=a.device)
+            _lib.call("knerf_image_metrics", _lib.ptr(a), _lib.ptr(b), B, H, W, Cn, float(max_val), _lib.ptr(out[0]),
+                      _lib.ptr(out[1]), _lib.ptr(ws), n, _lib.stream())
+        else:
+            for i in range(B):
+                _lib.call("knerf_mse", _lib.ptr(a[i]), _lib.ptr(b[i]), a[i].numel(), out[0, i:i + 1].data_ptr(),
+                          _lib.stream())
+    out[0] = 20.0 * float(np.log10(max_val)) - 10.0 * torch.log10(out[0])
+    return out
 
 
 _seed_counter = itertools.count(0xC0A45E00)
@@ -354,12 +350,15 @@ class NeRF:
 
     # ---- metrics (nerf.py:306-330) ------------------------------------------------------------
     def update_and_return_metrics(self, images, coarse_images, fine_images, coarse_loss, fine_loss):
+        mc = image_metrics(images, coarse_images)
+        mf = image_metrics(images, fine_images)
+        vals = torch.stack([mc, mf]).cpu()                                        # one device -> host read
         self.coarse_loss_tracker.update_state(float(coarse_loss))
-        self.coarse_psnr_metric.update_state(_psnr(images, coarse_images).cpu())
-        self.corase_ssim_metric.update_state(_ssim(images, coarse_images).cpu())
+        self.coarse_psnr_metric.update_state(vals[0, 0])
+        self.corase_ssim_metric.update_state(vals[0, 1])
         self.fine_loss_tracker.update_state(float(fine_loss))
-        self.fine_psnr_metric.update_state(_psnr(images, fine_images).cpu())
-        self.fine_ssim_metric.update_state(_ssim(images, fine_images).cpu())
+        self.fine_psnr_metric.update_state(vals[1, 0])
+        self.fine_ssim_metric.update_state(vals[1, 1])
         return {m.name: m.result() for m in self.metrics}
 
     # ---- training (nerf.py:332-473) -----------------------------------------------------------

@@ -1,4 +1,5 @@
-"""CPU oracle (TEST INFRASTRUCTURE ONLY) for ImageLoader.__call__ -- keras_nerf/data/image.py:17-35.
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for ImageLoader.__call__ -- keras_nerf/data/image.py:17-35 -- and for the
+per-image PSNR / SSIM of NeRF.update_and_return_metrics -- keras_nerf/model/nerf/nerf.py:306-330 (bottom of file).
 
 The arithmetic lives in TensorFlow (>= 2.9, requirements.txt:2, absent offline):
   * tf.image.convert_image_dtype(uint8 -> float32): cast, then multiply by float32(1/255);
@@ -10,7 +11,7 @@ The arithmetic lives in TensorFlow (>= 2.9, requirements.txt:2, absent offline):
 This file restates that published algorithm in NumPy float32.  PARITY UNPINNED against TF itself (TF is not
 installed and the reference's image tests need the nerf_synthetic dataset, tests/data/test_image.py:12-20);
 the structure (span ends, weights, normalisation) is cross-checked against Pillow's independent
-antialiased-bilinear resampler in tests/test_image_loader_cpu.py.
+antialiased-bilinear resampler in tests/test_io_cpu.py.
 """
 from __future__ import annotations
 
@@ -80,3 +81,41 @@ def image_loader(rgba_u8: np.ndarray, image_width: int, image_height: int, white
     bg = np.ones_like(img[..., :3]) if white_background else np.zeros_like(img[..., :3])
     rgb = ((alpha * img[..., :3]).astype(F) + ((F(1.0) - alpha).astype(F) * bg).astype(F)).astype(F)
     return np.clip(np.concatenate([rgb, alpha], axis=-1), 0.0, 1.0).astype(F)
+
+
+# ---- tf.image.psnr / tf.image.ssim (keras_nerf/model/nerf/nerf.py:306-330) ----------------------------------------
+def psnr(a: np.ndarray, b: np.ndarray, max_val: float = 1.0) -> np.ndarray:
+    """tf.image.psnr: 20 log10(max_val) - 10 log10(mean over [H,W,C] of (a-b)^2), per image."""
+    mse = ((a.astype(F) - b.astype(F)) ** 2).reshape(a.shape[0], -1).mean(axis=1, dtype=np.float64)
+    return (20.0 * np.log10(max_val) - 10.0 * np.log10(mse)).astype(F)
+
+
+def ssim(a: np.ndarray, b: np.ndarray, max_val: float = 1.0, filter_size: int = 11, filter_sigma: float = 1.5,
+         k1: float = 0.01, k2: float = 0.03) -> np.ndarray:
+    """tf.image.ssim (image_ops_impl.py: _fspecial_gauss, _ssim_per_channel, _ssim_helper) on [B,H,W,C]:
+    the window is softmax(-(x^2 + y^2) / (2 sigma^2)) over the 11x11 grid, applied as a VALID depthwise
+    convolution to x, y, x*y and x^2 + y^2; luminance * cs averaged over positions, then channels."""
+    coords = np.arange(filter_size, dtype=F) - F(filter_size - 1) / F(2.0)
+    g = np.square(coords) * F(-0.5 / np.square(F(filter_sigma)))
+    g2 = (g.reshape(1, -1) + g.reshape(-1, 1)).astype(np.float64)
+    win = np.exp(g2 - g2.max())
+    win = (win / win.sum()).astype(F)                                      # tf.nn.softmax
+    a, b = a.astype(F), b.astype(F)
+    Ho, Wo = a.shape[1] - filter_size + 1, a.shape[2] - filter_size + 1
+
+    def reducer(x):
+        out = np.zeros((x.shape[0], Ho, Wo, x.shape[3]), dtype=F)
+        for dy in range(filter_size):
+            for dx in range(filter_size):
+                out += win[dy, dx] * x[:, dy:dy + Ho, dx:dx + Wo, :]
+        return out
+
+    c1, c2 = F((k1 * max_val) ** 2), F((k2 * max_val) ** 2)
+    mean0, mean1 = reducer(a), reducer(b)
+    num0 = mean0 * mean1 * F(2.0)
+    den0 = np.square(mean0) + np.square(mean1)
+    luminance = (num0 + c1) / (den0 + c1)
+    num1 = reducer(a * b) * F(2.0)
+    den1 = reducer(np.square(a) + np.square(b))
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (luminance * cs).mean(axis=(1, 2), dtype=np.float64).mean(axis=-1).astype(F)

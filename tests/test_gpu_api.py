@@ -58,7 +58,7 @@ def test_fit_reduces_loss_and_checkpoint_round_trip(precision, tmp_path):
     K, g, m, rays = _setup(precision)
     # a learnable target: the analytic sphere of the synthetic scene instead of noise
     from keras_nerf_b200.data.synthetic import analytic_rgba
-    img = analytic_rgba(torch.from_numpy(g["o"]).cuda(), torch.from_numpy(g["d"]).cuda(), True)[None]
+    img = analytic_rgba(torch.from_numpy(g["o"]).cuda(), torch.from_numpy(g["d"]).cuda(), True, albedo=1.0)[None]
     seen = []
 
     class Monitor:   # the two hooks NeRFTrainMonitor uses (callback.py:62,113)

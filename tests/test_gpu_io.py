@@ -105,3 +105,24 @@ def test_train_script_monitor_resume_and_inference_gif(tmp_path):
         assert 1 <= im.n_frames <= 4 and im.size == (16, 16)   # Pillow merges identical consecutive frames
     with pytest.raises(FileNotFoundError):
         inference.main(["--model_dirs", str(tmp_path / "empty")])
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 256, 3), (2, 16, 16, 3), (3, 37, 53, 3), (1, 11, 11, 1), (1, 400, 400, 3)])
+def test_image_metrics_kernel_matches_oracle(shape):
+    """per-image PSNR / SSIM of update_and_return_metrics (nerf.py:306-330) from knerf_image_metrics"""
+    from keras_nerf_b200.model.nerf.nerf import image_metrics
+    rng = np.random.default_rng(shape[1])
+    a = rng.random(shape, dtype=np.float32)
+    b = np.clip(a + 0.2 * rng.standard_normal(shape).astype(np.float32), 0, 1).astype(np.float32)
+    b[0, : shape[1] // 2] = a[0, : shape[1] // 2]                          # a flat-error region and a noisy one
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = image_metrics(ta, tb).cpu().numpy()
+    assert out.shape == (2, shape[0])
+    assert np.abs(out[0] - IO.psnr(a, b)).max() <= 1e-4                    # dB
+    assert np.abs(out[1] - IO.ssim(a, b)).max() <= 5e-6
+    again = image_metrics(ta, tb).cpu().numpy()
+    assert np.array_equal(out, again)                                      # fixed-order sums: bit-reproducible
+    same = image_metrics(ta, ta).cpu().numpy()
+    assert np.allclose(same[1], 1.0, atol=1e-6) and np.isinf(same[0]).all()
+    small = image_metrics(ta[:, -8:, -8:], tb[:, -8:, -8:]).cpu().numpy()  # below the window: PSNR only
+    assert np.isnan(small[1]).all() and np.abs(small[0] - IO.psnr(a[:, -8:, -8:], b[:, -8:, -8:])).max() <= 1e-4

@@ -164,3 +164,25 @@ def test_mimwrite_gif_round_trip(tmp_path):
         assert im.n_frames == 4 and im.size == (16, 16) and im.info["duration"] == 50
         im.seek(3)
         assert np.asarray(im.convert("RGB"))[0, 0].tolist() == [255, 255, 255]
+
+
+# ---- f1: oracle of tf.image.ssim ----------------------------------------------------------------------------------
+def test_ssim_oracle_properties_and_golden():
+    rng = np.random.default_rng(5)
+    a = rng.random((2, 24, 20, 3), dtype=np.float32)
+    b = np.clip(a + 0.1 * rng.standard_normal(a.shape).astype(np.float32), 0, 1)
+    assert np.allclose(IO.ssim(a, a), 1.0, atol=1e-6)
+    s_ab = IO.ssim(a, b)
+    assert np.allclose(s_ab, IO.ssim(b, a), atol=1e-6) and (s_ab < 0.99).all() and (s_ab > 0).all()
+    assert IO.ssim(a[:, :11, :11], b[:, :11, :11]).shape == (2,)           # exactly one window position
+    assert np.allclose(IO.psnr(a, b), -10 * np.log10(((a - b) ** 2).reshape(2, -1).mean(1)), atol=1e-4)
+    # the reference's own metric code (nerf.py:306-330) executed over the TF stand-in: golden s0_*_ssim / psnr
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "tfshim"))
+    try:
+        import tensorflow as tf                                             # the torch stand-in, not TensorFlow
+        ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+        assert np.allclose(np.asarray(tf.image.ssim(ta, tb, max_val=1.0)), s_ab, atol=2e-6)
+        assert np.allclose(np.asarray(tf.image.psnr(ta, tb, max_val=1.0)), IO.psnr(a, b), atol=1e-4)
+    finally:
+        sys.path.pop(0)
