@@ -62,7 +62,9 @@ def main(argv=None):
     frames = torch.stack(images) if images else torch.empty((0, args.img_wh, args.img_wh, 3), device=nerf.device)
     if strategy is not None:
         frames = strategy.gather_rows(frames, len(poses))
-        if strategy.rank != 0:
+        rank = strategy.rank
+        torch.distributed.destroy_process_group()
+        if rank != 0:
             return None
     os.makedirs(args.output_dir, exist_ok=True)
     logging.info("creating the video from the frames...")

@@ -161,7 +161,13 @@ class NeRFTrainMonitor:
                 save_figure(os.path.join(self.log_dir, f'test_{i}_{epoch}.png'), ci[i], cd[i], fi[i], fd[i],
                             self.images[i, ..., :3], curves, f'Loss Plot: {epoch}')
             # another view from the iterator (callback.py:176-214)
-            images, rays = self.dataset_iterator.get_next()
+            try:
+                images, rays = self.dataset_iterator.get_next()
+            except IndexError:
+                # the reference's iterator raises OutOfRangeError once the test split is used up (more logging epochs
+                # than test batches); here it starts over
+                self.dataset_iterator = iter(self.dataset)
+                images, rays = self.dataset_iterator.get_next()
             images = images[..., :3]
             o, d, t = (r[:self.batch_size] for r in rays)
             coarse, fine = self.model.predict_and_render_images((o, d, t))

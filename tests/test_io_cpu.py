@@ -186,3 +186,25 @@ def test_ssim_oracle_properties_and_golden():
         assert np.allclose(np.asarray(tf.image.psnr(ta, tb, max_val=1.0)), IO.psnr(a, b), atol=1e-4)
     finally:
         sys.path.pop(0)
+
+
+# ---- train.py: per-replica slices of the global batch (MirroredStrategy semantics, train.py:75-87) ------------
+def test_replica_batches_split_the_global_batch():
+    import train
+
+    class FakeStrategy:
+        def __init__(self, rank):
+            self.rank, self.num_replicas_in_sync = rank, 2
+
+    per_rank = []
+    for rank in range(2):
+        ds, _ = _fake_dataset(9, 4)                        # global batch 4 = 2 replicas x batch_size 2
+        ds._rng.seed(42)                                   # what train.py does so that all ranks agree on the order
+        rb = train.ReplicaBatches(ds, FakeStrategy(rank), per_replica=2)
+        assert len(rb) == 2 and len(rb.take(1)) == 1 and iter(rb).get_next()[0].shape[0] == 2
+        per_rank.append([(im[:, 0, 0, 0].tolist(), o[:, 0, 0, 0].tolist()) for im, (o, d, t) in rb])
+    for b0, b1 in zip(*per_rank):
+        assert len(b0[0]) == len(b1[0]) == 2 and not set(b0[0]) & set(b1[0])   # disjoint halves of one batch
+        assert b0[0] == b0[1] and b1[0] == b1[1]
+    seen = [x for rank in per_rank for b in rank for x in b[0]]
+    assert len(seen) == 8 and len(set(seen)) == 8

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from keras_nerf_b200 import NeRF
-from keras_nerf_b200.data.loader import DatasetLoader
+from keras_nerf_b200.data.loader import DatasetLoader, _Iterator
 from keras_nerf_b200.model.nerf.callback import NeRFTrainMonitor
 
 
@@ -26,9 +26,12 @@ class ReplicaBatches:
         r, b = self.strategy.rank, self.per_replica
         return x[r * b:(r + 1) * b]
 
-    def __iter__(self):
+    def _batches(self):
         for images, rays in self.dataset:
             yield self._slice(images), tuple(self._slice(x) for x in rays)
+
+    def __iter__(self):
+        return _Iterator(self._batches())                    # next() and get_next(), like the loader's datasets
 
     def __len__(self):
         return len(self.dataset)
@@ -111,6 +114,9 @@ def main(argv=None, multi_gpu=True):
     if strategy is None or strategy.rank == 0:
         os.makedirs(args.model_dirs, exist_ok=True)
         nerf.save_model(os.path.join(args.model_dirs, args.name))
+    if strategy is not None:
+        strategy.barrier()
+        torch.distributed.destroy_process_group()
     return nerf
 
 
