@@ -102,6 +102,16 @@ class RayShardedStrategy:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item()) / self.num_replicas_in_sync
 
+    def mean_dict(self, logs: dict) -> dict:
+        """cross-replica mean of every value of a metrics dict in ONE all-reduce (Keras aggregates the `Mean` metric
+        variables of a MirroredStrategy over the replicas; every rank sees the same number of batches)"""
+        if self.num_replicas_in_sync == 1 or not logs:
+            return dict(logs)
+        keys = sorted(logs)
+        t = torch.tensor([float(logs[k]) for k in keys], dtype=torch.float64, device=self.device or "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return {k: float(v) / self.num_replicas_in_sync for k, v in zip(keys, t.tolist())}
+
     def barrier(self):
         if self.num_replicas_in_sync > 1:
             dist.barrier()

@@ -460,6 +460,8 @@ class NeRF:
                 for batch in validation_data:
                     vlogs = self.test_step(batch)
                 logs = {**logs, **{"val_" + k: v for k, v in vlogs.items()}}
+            if self.strategy is not None:
+                logs = self.strategy.mean_dict(logs)          # the epoch's logs are the mean over the replicas
             for k, v in logs.items():
                 history.setdefault(k, []).append(v)
             if verbose:

@@ -44,6 +44,8 @@ def _worker(rank, world, port, q):
     got = st.gather_rows(mine.clone(), H, 0)
     assert torch.equal(got, full)
     assert st.mean_scalar(float(rank)) == pytest.approx(sum(range(world)) / world)
+    md = st.mean_dict({"fine_loss": float(rank), "coarse_loss": 2.0 * rank + 1.0})
+    assert md == {"coarse_loss": pytest.approx(float(world)), "fine_loss": pytest.approx((world - 1) / 2.0)}
     # sharded rendering gathers whole ray chunks: uneven chunk counts per rank (5 chunks of 4 rays over 2 ranks)
     chunks, rc = 5, 4
     bounds = [st.shard_bounds_of(r, chunks) for r in range(world)]
@@ -53,6 +55,14 @@ def _worker(rank, world, port, q):
     lo, hi = st.shard_bounds(chunks)
     got = st.gather_rows(px[lo * rc:hi * rc].clone(), chunks * rc, 0, sizes=sizes)
     assert torch.equal(got, px)
+
+    # orbit frames sharded over ranks (inference.py, benchmarks/orbit.py): with fewer frames than ranks a rank
+    # holds an empty shard
+    for nf in (1, 3):
+        lo, hi = st.shard_bounds(nf)
+        frames = torch.arange(nf * 4, dtype=torch.float32).reshape(nf, 2, 2)
+        got = st.gather_rows(frames[lo:hi].clone(), nf)
+        assert torch.equal(got, frames)
 
     class Net:  # broadcast of replicated weights
         def __init__(self, v):

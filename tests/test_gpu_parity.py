@@ -607,3 +607,38 @@ def test_config2_4096_ray_step_properties():
     fd = (vals[0] - vals[1]) / 4e-3
     analytic = float((g1[n:].double() * direction.double()).sum())
     assert fd == pytest.approx(analytic, rel=5e-2, abs=1e-6)
+
+
+# ---- empty inputs and argument errors through the C ABI ------------------------------------------------------
+def test_empty_inputs_and_argument_errors():
+    """R = 0 is a no-op for every per-ray entry point (a tf op on a [0, ...] tensor); bad arguments come back as a
+    negative status + message (KnerfError), never a crash."""
+    gpu()
+    from keras_nerf_b200 import _lib
+    dev = torch.device("cuda")
+    z = torch.zeros(16, device=dev)
+    st = _lib.stream()
+    P = _lib.ptr(z)
+    _lib.call("knerf_composite_forward", P, None, None, P, 0, 64, 1, 1, 1e-10, P, P, P, P, st)
+    _lib.call("knerf_composite_backward", P, P, 0, 64, 1, 1, 1e-10, None, P, 1.0, 1, P, P, st)
+    _lib.call("knerf_sample_fine", P, None, P, None, 1, None, 0, 64, 128, 0, P, None, None, None, None, st)
+    _lib.call("knerf_positional_encoding", P, 0, 3, 10, P, 63, st)
+    _lib.call("knerf_encode_position_and_directions", P, P, P, 0, 64, 10, 4, P, 63, P, 27, st)
+    _lib.call("knerf_uniform", P, 0, 1, 0, st)
+    _lib.call("knerf_adam_step", P, P, P, P, 0, 1e-3, 0.9, 0.999, 1e-7, 1, 1, st)
+    torch.cuda.synchronize()
+    assert float(z.abs().sum()) == 0.0                        # nothing was written
+    bad = [("knerf_composite_forward", (None, None, None, P, 4, 64, 1, 1, 1e-10, P, P, P, P, st)),      # no inputs
+           ("knerf_sample_fine", (P, P, P, None, 1, None, 1, 64, 128, 0, P, None, None, None, None, st)),  # both forms
+           ("knerf_sample_fine", (P, None, P, None, 1, None, 1, 1, 128, 0, P, None, None, None, None, st)),  # Nc < 2
+           ("knerf_sample_fine", (P, None, P, None, 1, None, 1, 64, 4096, 0, P, None, None, None, None, st)),  # Nf max
+           ("knerf_sample_fine", (P, None, P, None, 1, None, 1, 64, 128, 7, P, None, None, None, None, st)),  # oob_mode
+           ("knerf_generate_rays", (None, 4, 4, 100.0, 2.0, 6.0, 8, None, 1, P, P, P, st)),
+           ("knerf_generate_rays", (P, 0, 4, 100.0, 2.0, 6.0, 8, None, 1, P, P, P, st)),
+           ("knerf_image_metrics", (P, P, 1, 4, 4, 3, 1.0, P, P, P, 16, st))]                        # below the window
+    for name, args in bad:
+        with pytest.raises(_lib.KnerfError):
+            _lib.call(name, *args)
+        assert len(_lib.load().knerf_last_error()) > 0
+    with pytest.raises(_lib.KnerfError):                      # host tensors are refused before the call
+        _lib.ptr(torch.zeros(4))
