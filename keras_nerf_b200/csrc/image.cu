@@ -7,8 +7,9 @@
 // max(0, 1 - |pos| / kernel_scale) normalised to sum 1, rows resized first, columns second, every sum taken in
 // span order in fp32.  One thread per output pixel does exactly that for its 4 channels: for each column tap the
 // row sum (the value TF's intermediate [out_h, in_w] image holds), then the column sum.  The weights are
-// recomputed per tap (4 flops) instead of being tabulated; products and sums are left unfused (__fmul_rn /
-// __fadd_rn) so the result equals the two-pass fp32 formulation bit for bit.
+// computed in-kernel (registers for row spans of up to 8 taps, per tap beyond) instead of being tabulated;
+// products and sums are left unfused (__fmul_rn / __fadd_rn) so the result equals the two-pass fp32
+// formulation bit for bit.
 // HBM: reads the uint8 source once (4 B per source pixel; the taps of neighbouring outputs overlap in L1/L2),
 // writes 16 B per output pixel.
 #include "common.cuh"
@@ -58,17 +59,36 @@ __global__ void __launch_bounds__(256) image_prepare_kernel(const uchar4* __rest
   if (ox >= ax.out_size || oy >= ay.out_size) return;
   const Span sy = make_span(ay, oy), sx = make_span(ax, ox);
   const float k255 = 1.0f / 255.0f;   // convert_image_dtype: cast * (1 / 255)
+  // row weights do not depend on the column tap: spans of up to kRegTaps rows (reductions up to 3.5x) keep them
+  // in registers, longer ones recompute them per tap
+  constexpr int kRegTaps = 8;
+  float wy[kRegTaps];
+#pragma unroll
+  for (int k = 0; k < kRegTaps; ++k) wy[k] = (k < sy.n) ? tap_weight(ay, sy, k) : 0.f;
   float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
   for (int kx = 0; kx < sx.n; ++kx) {
     float ir = 0.f, ig = 0.f, ib = 0.f, ia = 0.f;   // the [oy, sx.start + kx] pixel of TF's row-resized image
     const uchar4* col = src + (size_t)sy.start * ax.in_size + (sx.start + kx);
-    for (int ky = 0; ky < sy.n; ++ky) {
-      const uchar4 p = __ldg(col + (size_t)ky * ax.in_size);
-      const float w = tap_weight(ay, sy, ky);
-      ir = __fadd_rn(ir, __fmul_rn(w, __fmul_rn((float)p.x, k255)));
-      ig = __fadd_rn(ig, __fmul_rn(w, __fmul_rn((float)p.y, k255)));
-      ib = __fadd_rn(ib, __fmul_rn(w, __fmul_rn((float)p.z, k255)));
-      ia = __fadd_rn(ia, __fmul_rn(w, __fmul_rn((float)p.w, k255)));
+    if (sy.n <= kRegTaps) {
+#pragma unroll
+      for (int ky = 0; ky < kRegTaps; ++ky) {
+        if (ky < sy.n) {
+          const uchar4 p = __ldg(col + (size_t)ky * ax.in_size);
+          ir = __fadd_rn(ir, __fmul_rn(wy[ky], __fmul_rn((float)p.x, k255)));
+          ig = __fadd_rn(ig, __fmul_rn(wy[ky], __fmul_rn((float)p.y, k255)));
+          ib = __fadd_rn(ib, __fmul_rn(wy[ky], __fmul_rn((float)p.z, k255)));
+          ia = __fadd_rn(ia, __fmul_rn(wy[ky], __fmul_rn((float)p.w, k255)));
+        }
+      }
+    } else {
+      for (int ky = 0; ky < sy.n; ++ky) {
+        const uchar4 p = __ldg(col + (size_t)ky * ax.in_size);
+        const float w = tap_weight(ay, sy, ky);
+        ir = __fadd_rn(ir, __fmul_rn(w, __fmul_rn((float)p.x, k255)));
+        ig = __fadd_rn(ig, __fmul_rn(w, __fmul_rn((float)p.y, k255)));
+        ib = __fadd_rn(ib, __fmul_rn(w, __fmul_rn((float)p.z, k255)));
+        ia = __fadd_rn(ia, __fmul_rn(w, __fmul_rn((float)p.w, k255)));
+      }
     }
     const float w = tap_weight(ax, sx, kx);
     r = __fadd_rn(r, __fmul_rn(w, ir));

@@ -9,45 +9,54 @@ struct Pose {
   float t[3];
 };
 
-// One thread per 4 consecutive samples of one ray (VEC=4) or per sample (VEC=1); the first thread of a
-// ray also emits origin and direction.  Consecutive threads write consecutive addresses of t.
+// One warp per 32 consecutive rays.  Phase 1: lane l computes origin and direction of ray base + l (every lane busy:
+// the two divisions, the normalisation and its three divisions cost the warp one pass per 32 rays instead of one per
+// ray).  Phase 2: the warp walks the 32 * N samples of those rays in units of VEC (4 = one 16-byte store), consecutive
+// lanes on consecutive addresses of t.  Index arithmetic is 32-bit.
 template <int VEC>
 __global__ void __launch_bounds__(256) rays_kernel(Pose pose, int H, int W, float focal, float near_,
                                                    float far_, int N, const float* __restrict__ u,
                                                    uint64_t seed, float* __restrict__ o,
                                                    float* __restrict__ d, float* __restrict__ t) {
-  const int per_ray = N / VEC;
-  const int64_t total = (int64_t)H * W * per_ray;
+  const uint32_t per_ray = (uint32_t)(N / VEC);
+  const uint32_t n_rays = (uint32_t)H * (uint32_t)W;
   const float Wf = (float)W, Hf = (float)H, Nf = (float)N;
   const float delta = __fdiv_rn(__fsub_rn(far_, near_), (float)(N - 1));   // tf.linspace step
   const float interval = __fdiv_rn(__fsub_rn(far_, near_), Nf);            // rays.py:120 (N, not N-1)
   const float half_iv = interval * 0.5f;
-  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total;
-       g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t ray = g / per_ray;
-    const int s0 = (int)(g - ray * per_ray) * VEC;
-    if (s0 == 0) {
-      const int y = (int)(ray / W), x = (int)(ray - (int64_t)y * W);
-      // rays.py:89-94 -- no pixel-centre offset; cam = (xc, -yc, -1)
-      const float xc = __fdiv_rn(__fsub_rn((float)x, Wf * 0.5f), focal);
-      const float yc = __fdiv_rn(__fsub_rn((float)y, Hf * 0.5f), focal);
-      float dir[3];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t base = warp * 32; base < n_rays; base += n_warps * 32) {
+    {
+      const uint32_t ray = base + lane;
+      if (ray < n_rays) {
+        const uint32_t y = ray / (uint32_t)W, x = ray - y * (uint32_t)W;
+        // rays.py:89-94 -- no pixel-centre offset; cam = (xc, -yc, -1)
+        const float xc = __fdiv_rn(__fsub_rn((float)x, Wf * 0.5f), focal);
+        const float yc = __fdiv_rn(__fsub_rn((float)y, Hf * 0.5f), focal);
+        float dir[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        // rays.py:103-107: broadcast multiply then reduce_sum over j = 0,1,2 (products rounded separately)
-        const float p0 = __fmul_rn(xc, pose.r[i][0]);
-        const float p1 = __fmul_rn(-yc, pose.r[i][1]);
-        const float p2 = __fmul_rn(-1.0f, pose.r[i][2]);
-        dir[i] = __fadd_rn(__fadd_rn(p0, p1), p2);
-      }
-      const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])),
-                                             __fmul_rn(dir[2], dir[2])));
+        for (int i = 0; i < 3; ++i) {
+          // rays.py:103-107: broadcast multiply then reduce_sum over j = 0,1,2 (products rounded separately)
+          const float p0 = __fmul_rn(xc, pose.r[i][0]);
+          const float p1 = __fmul_rn(-yc, pose.r[i][1]);
+          const float p2 = __fmul_rn(-1.0f, pose.r[i][2]);
+          dir[i] = __fadd_rn(__fadd_rn(p0, p1), p2);
+        }
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])),
+                                               __fmul_rn(dir[2], dir[2])));
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        d[ray * 3 + i] = __fdiv_rn(dir[i], nrm);   // rays.py:108-109
-        o[ray * 3 + i] = pose.t[i];                // rays.py:112-113
+        for (int i = 0; i < 3; ++i) {
+          d[(size_t)ray * 3 + i] = __fdiv_rn(dir[i], nrm);   // rays.py:108-109
+          o[(size_t)ray * 3 + i] = pose.t[i];                // rays.py:112-113
+        }
       }
     }
+    const uint32_t units = min(32u, n_rays - base) * per_ray;
+    for (uint32_t unit = lane; unit < units; unit += 32) {
+    const uint32_t r = unit / per_ray;
+    const int s0 = (int)(unit - r * per_ray) * VEC;
+    const int64_t ray = (int64_t)base + r;
     float uu[VEC];
     const int64_t e0 = ray * N + s0;
     if (u != nullptr) {
@@ -82,6 +91,7 @@ __global__ void __launch_bounds__(256) rays_kernel(Pose pose, int H, int W, floa
       *reinterpret_cast<float4*>(t + e0) = make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]);
     } else {
       t[e0] = out[0];
+    }
     }
   }
 }
@@ -119,8 +129,9 @@ extern "C" int knerf_generate_rays(const float* c2w_host, int H, int W, float fo
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (n_samples % 4 == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0) &&
                    (u == nullptr || (reinterpret_cast<uintptr_t>(u) & 15) == 0);
-  const int64_t total = (int64_t)H * W * (vec ? n_samples / 4 : n_samples);
-  const int grid = (int)std::min<int64_t>(cdiv(total, 256), (int64_t)kNumSMs * 16);
+  KN_CHECK_ARG((int64_t)H * W < (int64_t)1 << 31 && (int64_t)n_samples * 32 < (int64_t)1 << 31,
+               "knerf_generate_rays: image too large (%d x %d)", H, W);
+  const int grid = (int)std::min<int64_t>(cdiv((int64_t)H * W, 256), (int64_t)kNumSMs * 16);
   if (vec)
     rays_kernel<4><<<grid, 256, 0, st>>>(p, H, W, focal, near_, far_, n_samples, u, seed, o, d, t);
   else

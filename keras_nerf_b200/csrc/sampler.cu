@@ -48,6 +48,36 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&v)[P], int lane) {
   }
 }
 
+// Level-order (Eytzinger) slot of sorted position p in a complete tree of 2^LOG - 1 nodes stored at [1, 2^LOG):
+// the nodes of one level are contiguous, so the 32 lanes' probes of a search level fall into consecutive
+// shared-memory banks (a plain binary search probes addresses = step - 1 mod 2*step: one or two banks per level).
+__device__ __forceinline__ int eyt_slot(int p, int LOG) {
+  const int t = __ffs(p + 1) - 1;
+  return (1 << (LOG - 1 - t)) + ((p + 1) >> (t + 1));
+}
+
+// #{entries <= v} (INCL) or #{entries < v} of the tree `e` (2^LOG - 1 nodes, missing ones = +inf), for NQ
+// independent queries at once (interleaved LDS chains)
+template <int LOG, int NQ, bool INCL>
+__device__ __forceinline__ void eyt_count(const float* e, const float (&v)[NQ], int (&cnt)[NQ]) {
+  int k[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) k[q] = 1;
+#pragma unroll
+  for (int l = 0; l < LOG; ++l) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float x = e[k[q]];
+      k[q] = 2 * k[q] + ((INCL ? (x <= v[q]) : (x < v[q])) ? 1 : 0);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) cnt[q] = k[q] - (1 << LOG);
+}
+
+template <int N> struct Log2 { static constexpr int value = 1 + Log2<N / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
 struct SampleArgs {
   const float* t_coarse; const float* mid_points; const float* weights; const float* u;
   uint64_t seed; const float* cdf_in; int64_t R; int Nc; int Nf; int oob_mode; int sequential;
@@ -61,17 +91,19 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int Nc = a.Nc, Nf = a.Nf;
   const int nc1 = (Nc + 1 + 3) & ~3;
-  // cdf and the coarse depths are padded with +inf to CAP (a power of two > Nc + 1): every search below is a
-  // fixed-depth branchless upper bound, all of a lane's searches interleaved (independent LDS chains).
-  constexpr int CAP = 64 * NCB;
-  float* cdf = smem + (size_t)wib * a.smem_per_warp;   // [CAP]: Nc+1 entries + inf
-  float* tcs = cdf + CAP;                              // [CAP]: Nc entries + inf
-  float* midp = tcs + CAP;                             // [Nc+1]: Nc-1 mid points + 2 out-of-range slots
-  float* fs = midp + nc1;                              // [32*P] sorted fine samples (+inf beyond Nf)
-  float* outs = fs + 32 * P;                           // [Nc+Nf]
+  // Searches run over level-order copies (eyt_slot) of the cdf, the coarse depths and the sorted fine samples,
+  // padded with +inf to a complete tree: fixed depth, branchless, conflict-free, all of a lane's searches interleaved.
+  constexpr int CAP = 64 * NCB;                        // > Nc + 1
+  constexpr int LOGC = Log2<CAP>::value, LOGF = Log2<32 * P>::value;
+  float* cdf = smem + (size_t)wib * a.smem_per_warp;   // [Nc+1] linear (gathers, cdf_out)
+  float* cdf_e = cdf + nc1;                            // [CAP] level order
+  float* tcs_e = cdf_e + CAP;                          // [CAP] level order, Nc coarse depths
+  float* midp = tcs_e + CAP;                           // [Nc+1]: Nc-1 mid points + 2 out-of-range slots
+  float* fs_e = midp + nc1;                            // [32*P] level order: the first 32P-1 sorted fine samples
+  float* outs = fs_e + 32 * P;                         // [Nc+Nf]
   const int64_t nwarps = (int64_t)gridDim.x * kSampWarps;
-  for (int i = Nc + 1 + lane; i < CAP; i += 32) cdf[i] = CUDART_INF_F;
-  for (int i = Nc + lane; i < CAP; i += 32) tcs[i] = CUDART_INF_F;
+  for (int i = lane; i < CAP; i += 32) { cdf_e[i] = CUDART_INF_F; tcs_e[i] = CUDART_INF_F; }
+  __syncwarp();
   // 4 consecutive draws per lane (one 16-byte load / one Philox block) when the row length allows it
   const bool vec4 = (P >= 4) && (Nf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.u) & 15) == 0);
 
@@ -138,15 +170,18 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
           if (lane == 31) tn = first_next;
         }
         if (i < Nc - 1) midp[i] = 0.5f * __fadd_rn(tn, tc[j]);
-        if (i < Nc) tcs[i] = tc[j];
+        if (i < Nc) tcs_e[eyt_slot(i, LOGC)] = tc[j];
       }
     } else {
       for (int i = lane; i < Nc - 1; i += 32) midp[i] = a.mid_points[ray * (Nc - 1) + i];
     }
     __syncwarp();
     if (lane < 2) midp[Nc - 1 + lane] = (a.oob_mode == KNERF_OOB_CLAMP && Nc >= 2) ? midp[Nc - 2] : 0.f;
-    if (a.cdf_out != nullptr && live)
-      for (int i = lane; i <= Nc; i += 32) a.cdf_out[ray * (Nc + 1) + i] = cdf[i];
+    for (int i = lane; i <= Nc; i += 32) {
+      const float c = cdf[i];
+      cdf_e[eyt_slot(i, LOGC)] = c;
+      if (a.cdf_out != nullptr && live) a.cdf_out[ray * (Nc + 1) + i] = c;
+    }
     __syncwarp();
 
     // ---- inverse-CDF samples (utils.py:72-94) ---------------------------------------------------
@@ -180,13 +215,7 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
       }
     }
     int idx[P];                                       // searchsorted(cdf, u, side='right') = #{cdf_j <= u}
-#pragma unroll
-    for (int r = 0; r < P; ++r) idx[r] = 0;
-#pragma unroll
-    for (int step = CAP / 2; step >= 1; step >>= 1) {
-#pragma unroll
-      for (int r = 0; r < P; ++r) idx[r] += (cdf[idx[r] + step - 1] <= uu[r]) ? step : 0;
-    }
+    eyt_count<LOGC, P, true>(cdf_e, uu, idx);
     int oob = 0;
 #pragma unroll
     for (int r = 0; r < P; ++r) {
@@ -215,17 +244,15 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
     // ---- sort(concat(t_coarse, samples)) (nerf.py:190-191) -------------------------------------
     bitonic_sort_regs<P>(s, lane);
 #pragma unroll
-    for (int r = 0; r < P; ++r) fs[lane * P + r] = s[r];
+    for (int r = 0; r < P; ++r) {
+      const int e = lane * P + r;
+      if (e < 32 * P - 1) fs_e[eyt_slot(e, LOGF)] = s[r];
+    }
+    const float fs_last = __shfl_sync(kFullMask, s[P - 1], 31);   // sorted position 32P-1 (not in the tree)
     __syncwarp();
     {
       int cnt[P];                                     // coarse entries <= v (a fine sample goes after equal coarse ones)
-#pragma unroll
-      for (int r = 0; r < P; ++r) cnt[r] = 0;
-#pragma unroll
-      for (int step = CAP / 2; step >= 1; step >>= 1) {
-#pragma unroll
-        for (int r = 0; r < P; ++r) cnt[r] += (tcs[cnt[r] + step - 1] <= s[r]) ? step : 0;
-      }
+      eyt_count<LOGC, P, true>(tcs_e, s, cnt);
 #pragma unroll
       for (int r = 0; r < P; ++r) {
         const int e = lane * P + r;
@@ -234,17 +261,11 @@ __global__ void __launch_bounds__(kSampWarps * 32) sample_fine_kernel(SampleArgs
     }
     {
       int cnt[NCB];                                   // fine entries < v
-#pragma unroll
-      for (int j = 0; j < NCB; ++j) cnt[j] = 0;
-#pragma unroll
-      for (int step = 16 * P; step >= 1; step >>= 1) {
-#pragma unroll
-        for (int j = 0; j < NCB; ++j) cnt[j] += (fs[cnt[j] + step - 1] < tc[j]) ? step : 0;
-      }
+      eyt_count<LOGF, NCB, false>(fs_e, tc, cnt);
 #pragma unroll
       for (int j = 0; j < NCB; ++j) {
         const int i = j * 32 + lane;
-        cnt[j] += (fs[cnt[j]] < tc[j]) ? 1 : 0;       // the search above tops out at 32P-1; all 32P may be smaller
+        cnt[j] += (fs_last < tc[j]) ? 1 : 0;          // all 32P-1 tree entries smaller is implied when the last one is
         if (i < Nc) outs[i + cnt[j]] = tc[j];
       }
     }
@@ -296,7 +317,7 @@ extern "C" int knerf_sample_fine(const float* t_coarse, const float* mid_points,
                t_sorted, samples, indices, cdf_out, oob_count, 0};
   const int nc1 = (Nc + 1 + 3) & ~3;
   const int cap = 64 * (ncb <= 2 ? ncb : (ncb <= 4 ? 4 : 8));
-  a.smem_per_warp = 2 * cap + nc1 + 32 * P + ((Nc + Nf + 3) & ~3);
+  a.smem_per_warp = 2 * nc1 + 2 * cap + 32 * P + ((Nc + Nf + 3) & ~3);
   const size_t smem = (size_t)a.smem_per_warp * kSampWarps * sizeof(float);
   const int grid = (int)std::min<int64_t>(cdiv(R, kSampWarps), (int64_t)kNumSMs * 12);
   cudaStream_t st = (cudaStream_t)stream;
