@@ -143,8 +143,9 @@ def run_reference(args):
 
 
 def workload_config(precision, ray_chunks):
-    return {"workload": "BASELINE config[3]: coarse+fine NeRF train step, 32768 rays/GPU from 400x400 synthetic "
-                        "orbit views (64 coarse + 128 fine samples, 8x256 MLPs, white bg, Adam), ray-sharded DP",
+    return {"workload": "BASELINE config[3]: coarse+fine NeRF train step, 32768 rays/GPU (128x256 crops of 400x400 "
+                        "synthetic orbit views mixing object and background; training stays alive: losses fall), "
+                        "64 coarse + 128 fine samples, 8x256 MLPs, white bg, Adam, ray-sharded DP",
             "rays_per_gpu": RAYS_PER_GPU, "image_wh": IMG_WH, "n_coarse": N_COARSE, "n_fine": N_FINE,
             "precision_mode": precision, "ray_chunks": ray_chunks,
             "l2": "per-step working set (activations of 6.3M samples) is >> 126 MB L2; inputs rotate over 4 batches"}

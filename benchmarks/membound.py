@@ -81,6 +81,14 @@ def main():
                                        _lib.ptr(dst), _lib.stream()))
         report(f"image_prepare {ih}x{iw} -> {oh}x{ow} (per output pixel)", 16 + 4.0 * ih * iw / (oh * ow), ms,
                rays=oh * ow)
+    for B_, H_, W_ in ((1, 128, 256), (4, 800, 800)):
+        x = torch.rand(B_, H_, W_, 3, device=dev)
+        y = torch.rand(B_, H_, W_, 3, device=dev)
+        nws = _lib.load().knerf_image_metrics_workspace_floats(B_, H_, W_, 3)
+        ws, res = torch.empty(nws, device=dev), torch.empty(2, B_, device=dev)
+        ms = time_ms(lambda: _lib.call("knerf_image_metrics", _lib.ptr(x), _lib.ptr(y), B_, H_, W_, 3, 1.0, _lib.ptr(res[0]),
+                                       _lib.ptr(res[1]), _lib.ptr(ws), nws, _lib.stream()))
+        report(f"image_metrics (MSE + SSIM) {B_}x{H_}x{W_}x3 (per pixel)", 24, ms, rays=B_ * H_ * W_)
     n = 2 * 595844
     pbuf, gbuf, mbuf, vbuf = (torch.zeros(n, device=dev) for _ in range(4))
     ms = time_ms(lambda: _lib.call("knerf_adam_step", _lib.ptr(pbuf), _lib.ptr(gbuf), _lib.ptr(mbuf), _lib.ptr(vbuf), n, 1e-3,
