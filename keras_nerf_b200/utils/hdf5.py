@@ -21,7 +21,7 @@ check the byte-level structures named above).  Host-side file I/O, not part of t
 from __future__ import annotations
 
 import struct
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
