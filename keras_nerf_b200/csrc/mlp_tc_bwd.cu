@@ -231,7 +231,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
 // =============================================================================================================
 constexpr int kWUnitBytes = 32768;     // 16 chunks x 128 samples x 16 B: 128 features (A) or 128 outputs (B)
 constexpr int kWSlots = 7;            // 7 x 32 KB in flight per CTA (224 KB of the 227 KB)
-constexpr int kWThreads = 192;         // warp 0 producer, warp 1 MMA, warps 2-5 flush
+constexpr int kWThreads = 224;         // warp 0 producer, warps 1 and 6 MMA issuers, warps 2-5 flush
 constexpr int kNumTasks = 10;
 constexpr int kWMaxUnits = 6;
 
@@ -240,8 +240,9 @@ constexpr int kWMaxUnits = 6;
 // are the bias gradient of that layer
 struct WUnit { int src, off, bytes, bias_layer, bias_col0, off2, bytes2; };
 // accumulator group: A = unit a (+ a_sub bytes), B = unit b (+ b_sub bytes)
-struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b, a_sub, b_sub; };
-struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; };
+struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b, a_sub, b_sub, issuer; };
+// last_grp[x][k]: the last group of issuer x that reads unit k (the one after which x releases the slot), -1 = none
+struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; int8_t last_grp[2][kWMaxUnits]; };
 // mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
 //      3: X = h7^T dG into the fp32 scratch (tc_finish_kernel turns it into dW_features and dW_rgb_features[:256])
 
@@ -301,6 +302,22 @@ static WTaskTable build_task_table() {
     t.g[4] = {2, 1, 256, 128, 10, 256, 27, 0, 0, 0, 1, 0, 0};
     t.g[5] = {4, 2, 416, 16, 11, 0, 128, 0, 2, 1, 1, 0, 8192};
     t.cost = 170;
+    // the three N = 128 groups are the heavy ones: two on issuer 0, the third with the three N = 16 groups on issuer 1
+    t.g[0].issuer = 0; t.g[2].issuer = 0; t.g[1].issuer = 1; t.g[3].issuer = 1; t.g[4].issuer = 1; t.g[5].issuer = 1;
+  }
+  // Two MMA-issuing threads (tcgen05.mma holds its issuer for ~160 cycles per N = 128 MMA whose pipe time is 64):
+  // every accumulator group belongs to ONE issuer, so the fp32 accumulation order of each gradient element -- and
+  // with it every bit -- is that of a single issuer.  Default split: groups alternate.
+  for (int k = 0; k < n; ++k) {
+    WTask& t = T.t[k];
+    if (k != n - 1)
+      for (int gi = 0; gi < t.n_groups; ++gi) t.g[gi].issuer = gi & 1;
+    for (int x = 0; x < 2; ++x)
+      for (int u = 0; u < kWMaxUnits; ++u) {
+        t.last_grp[x][u] = -1;
+        for (int gi = 0; gi < t.n_groups; ++gi)
+          if (t.g[gi].issuer == x && (t.g[gi].a == u || t.g[gi].b == u)) t.last_grp[x][u] = (int8_t)gi;
+      }
   }
   return T;
 }
@@ -346,8 +363,9 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     // a slot is free again when the MMAs that read it have completed AND the flush warps are done with it
-    for (int i = 0; i < kWSlots; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 2); }
-    mbar_init(&sm.acc_done, 1);
+    // (one release per issuer + one from the flush warps)
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 3); }
+    mbar_init(&sm.acc_done, 2);
     mbar_init(&sm.acc_free, 128);
     fence_mbar_init();
   }
@@ -376,8 +394,9 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
     if (lane == 0) {
+      const int me = (warp == 1) ? 0 : 1;
       uint32_t it = 0, free_par = 0;
       bool first_item = true;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -393,6 +412,7 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
         for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile, it += t.n_units) {
           for (int gi = 0; gi < t.n_groups; ++gi) {
             const WGroup& g = t.g[gi];
+            if (g.issuer != me) continue;
             const uint32_t ia = it + g.a, ib = it + g.b;
             const uint32_t sa = ia % kWSlots, sb = ib % kWSlots;
             mbar_wait(&sm.full[sa], (ia / kWSlots) & 1);
@@ -406,8 +426,16 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               const uint64_t db = umma_smem_desc(b_base + k * 256, 128, kChunkA);
               umma_bf16(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
             }
-            if (g.free_a) umma_commit(&sm.empty[sa]);
-            if (g.free_b) umma_commit(&sm.empty[sb]);
+            if (t.last_grp[me][g.a] == gi) umma_commit(&sm.empty[sa]);
+            if (t.last_grp[me][g.b] == gi) umma_commit(&sm.empty[sb]);
+          }
+          // units this issuer never reads: release them too (after their load has landed, so that the arrival
+          // counts for this use of the slot and not for the previous one)
+          for (int k = 0; k < t.n_units; ++k) {
+            if (t.last_grp[me][k] >= 0) continue;
+            const uint32_t iu = it + k;
+            mbar_wait(&sm.full[iu % kWSlots], (iu / kWSlots) & 1);
+            mbar_arrive(&sm.empty[iu % kWSlots]);
           }
         }
         umma_commit(&sm.acc_done);
