@@ -116,7 +116,11 @@ def stream() -> int:
 
 
 def dev(x, device, dtype=torch.float32) -> torch.Tensor:
-    """numpy / torch (any device) -> contiguous tensor on `device`."""
+    """numpy / torch / any DLPack producer (tf.Tensor via tf.experimental.dlpack, cupy, jax ...; any device) ->
+    contiguous tensor on `device`.  A DLPack producer that already lives on `device` is consumed zero-copy: this is
+    the shim a TensorFlow caller goes through."""
+    if not torch.is_tensor(x) and hasattr(x, "__dlpack__") and not hasattr(x, "__array_interface__"):
+        x = torch.from_dlpack(x)
     return torch.as_tensor(x, dtype=dtype, device=device).contiguous()
 
 

@@ -108,3 +108,32 @@ def test_rays_generator_feeds_model_like_inference_script():
         assert fine["weights"].shape == (1, wh, wh, 192)
         assert float(fine["image"].min()) >= 0.0 and float(fine["image"].max()) <= 1.0
     assert not torch.equal(frames[0], frames[1])
+
+
+def test_class_api_accepts_dlpack_producers():
+    """The shim consumes any DLPack producer zero-copy (how a tf.Tensor reaches libknerf): the same
+    render from torch tensors and from objects that expose only __dlpack__."""
+    K, g, m, rays = _setup()
+
+    class Foreign:
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None, **kw):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    dev = m.device
+    t_rays = tuple(torch.as_tensor(r).to(dev) for r in rays)
+    u = torch.as_tensor(g["u_fine"]).to(dev)
+    a = m.predict_and_render_images(t_rays, u_fine=u)
+    b = m.predict_and_render_images(tuple(Foreign(r) for r in t_rays), u_fine=Foreign(u))
+    assert torch.equal(a[1]["image"], b[1]["image"]) and torch.equal(a[0]["depth"], b[0]["depth"])
+    ut = K.NeRFUtils(1, 1, 8, 8, 10, 4, True)
+    rgb, sig = torch.rand(8, 16, 3, device=dev), torch.rand(8, 16, 1, device=dev)
+    t = torch.sort(torch.rand(8, 16, device=dev) * 4 + 2, dim=-1).values
+    o1 = ut.render_image_depth_chunk(rgb, sig, t)
+    o2 = ut.render_image_depth_chunk(Foreign(rgb), Foreign(sig), Foreign(t))
+    assert all(torch.equal(x, y) for x, y in zip(o1, o2))

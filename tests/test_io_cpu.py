@@ -208,3 +208,25 @@ def test_replica_batches_split_the_global_batch():
         assert b0[0] == b0[1] and b1[0] == b1[1]
     seen = [x for rank in per_rank for b in rank for x in b[0]]
     assert len(seen) == 8 and len(set(seen)) == 8
+
+
+# ---- the DLPack side of the shim ------------------------------------------------------------------------------
+class _Foreign:
+    """a tensor of 'another framework': exposes only the DLPack protocol (what tf.Tensor / cupy / jax arrays do)"""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None, **kw):
+        return self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_dev_accepts_dlpack_producers():
+    from keras_nerf_b200 import _lib
+    src = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    out = _lib.dev(_Foreign(src), torch.device("cpu"))
+    assert torch.equal(out, src) and out.data_ptr() == src.data_ptr()      # zero-copy on the same device
+    assert torch.equal(_lib.dev(np.arange(4.0), torch.device("cpu")), torch.arange(4, dtype=torch.float32))
