@@ -77,10 +77,21 @@ composite_fwd_kernel(const float* __restrict__ rgbsigma, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  // Short rays (S <= 64) carry only 1.3 KB per warp: the next ray of the warp is fetched before this one is
+  // composited, which doubles the bytes in flight per SM (a long ray already fills the memory pipeline by itself).
+  constexpr bool kPrefetch = NB <= 2;
+  float4 c[NB], c_next[NB];
+  float tt[NB], tt_next[NB];
+  if (kPrefetch && warp0 < R) load_ray<NB, PACKED>(rgbsigma, rgb, sigma, t, warp0, S, lane, c_next, tt_next);
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
-    float4 c[NB];
-    float tt[NB], delta[NB], ex[NB], e[NB], T[NB], w[NB];
-    load_ray<NB, PACKED>(rgbsigma, rgb, sigma, t, ray, S, lane, c, tt);
+    float delta[NB], ex[NB], e[NB], T[NB], w[NB];
+    if (kPrefetch) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { c[j] = c_next[j]; tt[j] = tt_next[j]; }
+      if (ray + nwarps < R) load_ray<NB, PACKED>(rgbsigma, rgb, sigma, t, ray + nwarps, S, lane, c_next, tt_next);
+    } else {
+      load_ray<NB, PACKED>(rgbsigma, rgb, sigma, t, ray, S, lane, c, tt);
+    }
     transmittance<NB>(c, tt, S, lane, eps, delta, ex, e, T, w);
     float cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
 #pragma unroll
@@ -120,10 +131,19 @@ composite_bwd_kernel(const float* __restrict__ rgbsigma, const float* __restrict
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   const float bg = white ? 1.0f : 0.0f;
+  constexpr bool kPrefetch = NB <= 2;   // as in the forward kernel (no gain for longer rays: measured)
+  float4 c[NB], c_next[NB];
+  float tt[NB], tt_next[NB];
+  if (kPrefetch && warp0 < R) load_ray<NB, true>(rgbsigma, nullptr, nullptr, t, warp0, S, lane, c_next, tt_next);
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
-    float4 c[NB];
-    float tt[NB], delta[NB], ex[NB], e[NB], T[NB], w[NB];
-    load_ray<NB, true>(rgbsigma, nullptr, nullptr, t, ray, S, lane, c, tt);
+    float delta[NB], ex[NB], e[NB], T[NB], w[NB];
+    if (kPrefetch) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { c[j] = c_next[j]; tt[j] = tt_next[j]; }
+      if (ray + nwarps < R) load_ray<NB, true>(rgbsigma, nullptr, nullptr, t, ray + nwarps, S, lane, c_next, tt_next);
+    } else {
+      load_ray<NB, true>(rgbsigma, nullptr, nullptr, t, ray, S, lane, c, tt);
+    }
     transmittance<NB>(c, tt, S, lane, eps, delta, ex, e, T, w);
     float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f;
 #pragma unroll
