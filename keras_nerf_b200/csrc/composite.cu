@@ -122,7 +122,7 @@ composite_fwd_kernel(const float* __restrict__ rgbsigma, const float* __restrict
 //   dL/dsigma_i  = dL/dalpha_i * delta_i * exp(-sigma_i delta_i)
 // through_act folds rgb=sigmoid(.), sigma=relu(.) derivatives in.
 template <int NB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (NB >= 3 && NB <= 6) ? 4 : 0)
 composite_bwd_kernel(const float* __restrict__ rgbsigma, const float* __restrict__ t, int64_t R, int S,
                      int white, int clip, float eps, const float* __restrict__ dimage,
                      const float* __restrict__ target, float loss_scale, int through_act,
