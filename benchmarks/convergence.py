@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--img_wh", type=int, default=100)
     ap.add_argument("--views", type=int, default=24)
     ap.add_argument("--white_bg", action="store_true")
+    ap.add_argument("--ray_chunks", type=int, default=0, help="default: the whole view in one chunk")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import inference
@@ -29,7 +30,7 @@ def main():
     tmp = a.out or tempfile.mkdtemp(prefix="knerf_conv_")
     data = write_nerf_synthetic_like(os.path.join(tmp, "scene"), image_wh=2 * a.img_wh, n_train=a.views, n_val=2, n_test=4)
     argv = ["--name", "ball", "--data_dir", data, "--img_wh", str(a.img_wh), "--batch_size", "1", "--ray_chunks",
-            str(a.img_wh * a.img_wh), "--log_dir", os.path.join(tmp, "logs"), "--model_dirs", os.path.join(tmp, "model"),
+            str(a.ray_chunks or a.img_wh * a.img_wh), "--log_dir", os.path.join(tmp, "logs"), "--model_dirs", os.path.join(tmp, "model"),
             "--log_freq", str(max(a.epochs // 3, 1)), "--precision", a.precision, "--num_epochs", str(a.epochs)]
     if a.white_bg:
         argv.append("--white_bg")
@@ -39,7 +40,7 @@ def main():
     hist = nerf.history if hasattr(nerf, "history") else None
     rows = list(csv.DictReader(open(os.path.join(tmp, "logs", "ball", "log.csv"))))
     gif = inference.main(["--model_dirs", os.path.join(tmp, "model", "ball"), "--img_wh", str(a.img_wh), "--ray_chunks",
-                          str(a.img_wh * a.img_wh), "--output_freq", "30", "--output_dir", os.path.join(tmp, "out"),
+                          str(a.ray_chunks or a.img_wh * a.img_wh), "--output_freq", "30", "--output_dir", os.path.join(tmp, "out"),
                           "--precision", a.precision] + (["--white_bg"] if a.white_bg else []))
     print(json.dumps({"precision": a.precision, "img_wh": a.img_wh, "views": a.views, "epochs": a.epochs,
                       "white_bg": a.white_bg, "train_wall_s": round(dt, 1), "steps": a.views * a.epochs,
