@@ -10,7 +10,9 @@ max-over-ranks device time with inputs resident in HBM; `e2e` = the same through
 HOST buffers (H2D of images+rays and D2H of the metrics inside the timed region).
 
 --impl reference times the reference's CPU implementation of the same step: TensorFlow is not installable
-offline, so this is the CPU oracle (torch-CPU restatement, `oracle/`) on all host cores, on a bounded sample.
+offline, so this is the CPU oracle (torch-CPU restatement, `oracle/`) on all host cores.  It runs ONE step of the
+same 32,768-ray workload (BASELINE config[0]'s size: one coarse+fine train step, then one 128x128 render), once --
+about a minute of CPU work -- whatever --steps / --warmup say; the line reports steps = 1, warmup = 0.
 """
 import argparse
 import json
@@ -33,7 +35,8 @@ IMG_WH = 400
 N_COARSE, N_FINE = 64, 128
 FLOP_FWD_PER_SAMPLE = 1_186_816          # 593,408 MAC, unpadded shapes
 FLOP_TRAIN_PER_SAMPLE = 3_489_024        # fwd + wgrad + dgrad
-CPU_SAMPLE_RAYS = 1024                   # bounded sample for the CPU arms (about 10-30 s of CPU work)
+CPU_SAMPLE_RAYS = 8192                   # bounded sample of the cpu_baseline leg (about 10-30 s of CPU work)
+CPU_RAY_CHUNKS = 2048                    # BASELINE config[0]'s ray_chunks (train_single.py:17)
 
 
 def load_peaks():
@@ -94,7 +97,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------
 # CPU arms: the oracle (port of the TF reference) on the host cores, bounded sample
 # --------------------------------------------------------------------------------------------------------
-def cpu_train_rays_per_sec(n_rays=CPU_SAMPLE_RAYS, steps=1, warmup=0):
+def cpu_train_rays_per_sec(n_rays=CPU_SAMPLE_RAYS, steps=1, warmup=0, render=False):
+    """The oracle's train_step (torch-CPU fp32, all host cores) on `n_rays` rays of the bench workload: a
+    (n_rays/256) x 256 crop of a 400x400 synthetic view, 64 + 128 samples, white background, ray_chunks 2048."""
     import torch
     import oracle as O
     cores = os.cpu_count() or 1
@@ -102,50 +107,66 @@ def cpu_train_rays_per_sec(n_rays=CPU_SAMPLE_RAYS, steps=1, warmup=0):
     cfg = O.NerfConfig()
     rng = np.random.default_rng(42)
     pc, pf = O.init_params(cfg, rng), O.init_params(cfg, rng)
-    side = int(round(n_rays ** 0.5))
-    assert side * side == n_rays
+    ch, cw = n_rays // 256, 256
+    assert ch * cw == n_rays and ch <= IMG_WH
     focal = O.get_focal_from_fov(0.6911112070083618, IMG_WH)
     pose = O.pose_spherical(45.0, -30.0, 4.0)
     u_c = O.uniform24(np.random.default_rng(1234), (IMG_WH, IMG_WH, cfg.n_coarse))
     o, d, t = O.generate_rays(pose, IMG_WH, IMG_WH, focal, 2.0, 6.0, cfg.n_coarse, u_c)
-    lo = (IMG_WH - side) // 2
-    crop = lambda x: x[lo:lo + side, lo:lo + side][None].contiguous()  # noqa: E731
+    y0, x0 = (IMG_WH - ch) // 2, (IMG_WH - cw) // 2
+    crop = lambda x: x[y0:y0 + ch, x0:x0 + cw][None].contiguous()  # noqa: E731
     rays = (crop(o), crop(d), crop(t))
-    images = np.random.default_rng(3).uniform(0, 1, (1, side, side, 4)).astype(np.float32)
+    images = np.random.default_rng(3).uniform(0, 1, (1, ch, cw, 4)).astype(np.float32)
     u_f = O.uniform24(np.random.default_rng(5678), (n_rays, cfg.n_fine))
     ac, af = O.AdamState(), O.AdamState()
+    rc = min(CPU_RAY_CHUNKS, n_rays)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.train_step(pc, pf, ac, af, cfg, images, rays, u_f, min(256, n_rays), True)
+        out = O.train_step(pc, pf, ac, af, cfg, images, rays, u_f, rc, True)
         pc, pf = out["params_coarse"], out["params_fine"]
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return {"value": n_rays / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_rays}-ray coarse+fine train step ({side}x{side} crop of a 400x400 view, ray_chunks 256), "
-                      f"oracle/ torch-CPU fp32 restatement of the TF reference (TF unavailable offline), "
-                      f"{dt:.2f} s/step"}, dt
+    res = {"value": n_rays / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{steps} x {n_rays}-ray coarse+fine train step ({ch}x{cw} crop of a 400x400 view, ray_chunks {rc}), "
+                     f"oracle/ torch-CPU fp32 restatement of the TF reference (TF unavailable offline), "
+                     f"{dt:.2f} s/step"}
+    if render:   # BASELINE config[0]'s second half: one full 128x128 render
+        side = 128
+        f2 = O.get_focal_from_fov(0.6911112070083618, side)
+        u2 = O.uniform24(np.random.default_rng(4321), (side, side, cfg.n_coarse))
+        o2, d2, t2 = O.generate_rays(pose, side, side, f2, 2.0, 6.0, cfg.n_coarse, u2)
+        uf2 = O.uniform24(np.random.default_rng(8765), (side * side, cfg.n_fine))
+        t0 = time.perf_counter()
+        O.predict_and_render_images(pc, pf, cfg, (o2[None], d2[None], t2[None]), uf2, CPU_RAY_CHUNKS, True)
+        res["render_128x128_s"] = time.perf_counter() - t0
+    return res, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, dt = cpu_train_rays_per_sec(CPU_SAMPLE_RAYS, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    # the same workload as the b200 arm (32,768 rays per step = BASELINE config[0]'s 2 x 128 x 128), ONE step, once
+    cb, dt = cpu_train_rays_per_sec(RAYS_PER_GPU, steps=1, warmup=0, render=True)
+    cfg = workload_config("fp32", CPU_RAY_CHUNKS)
+    cfg["reference_arm"] = ("CPU: one step of the same 32,768-ray workload (+ one 128x128 render, BASELINE config[0]), "
+                            "run once; a GPU rank count does not apply")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+            "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config("fp32", None), "cpu_baseline": cb,
+            "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "render": {"metric": "render_s_per_frame_128x128", "value": cb.get("render_128x128_s"), "unit": "s"},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(precision, ray_chunks):
     return {"workload": "BASELINE config[3]: coarse+fine NeRF train step, 32768 rays/GPU (128x256 crops of 400x400 "
-                        "synthetic orbit views mixing object and background; training stays alive: losses fall), "
-                        "64 coarse + 128 fine samples, 8x256 MLPs, white bg, Adam, ray-sharded DP",
+                        "synthetic orbit views), 64 coarse + 128 fine samples, 8x256 MLPs, white bg, Adam, "
+                        "ray-sharded DP",
             "rays_per_gpu": RAYS_PER_GPU, "image_wh": IMG_WH, "n_coarse": N_COARSE, "n_fine": N_FINE,
             "precision_mode": precision, "ray_chunks": ray_chunks,
             "l2": "per-step working set (activations of 6.3M samples) is >> 126 MB L2; inputs rotate over 4 batches"}
@@ -253,16 +274,23 @@ def main():
     if strategy is not None:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms = tt.tolist()
+    # BASELINE's second metric, config[2]: 800x800 render, the frame's rays sharded over the N ranks (collective)
+    from benchmarks.roofline import dominant_kernel_roofline, render_ms_per_frame
+    render = None
+    if not args.no_render:
+        try:
+            render = render_ms_per_frame(precision, dev, strategy)
+        except Exception as e:  # the secondary metric must never take the headline down
+            render = {"error": str(e)[:200]}
     if rank != 0:
         if strategy is not None:
-            strategy.barrier()
+            strategy.barrier()      # rank 0 is timing the CPU baseline
             torch.distributed.destroy_process_group()
         return
     peaks = load_peaks()
     total_rays = RAYS_PER_GPU * world * args.steps
     value = total_rays / (ms * 1e-3)
     e2e_value = total_rays / (e2e_ms * 1e-3)
-    from benchmarks.roofline import dominant_kernel_roofline, render_ms_per_frame
     roof = dominant_kernel_roofline(model, precision, peaks)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -274,13 +302,9 @@ def main():
             "step_tflops": FLOP_TRAIN_PER_SAMPLE * (N_COARSE + N_COARSE + N_FINE) * RAYS_PER_GPU * world
             * args.steps / (ms * 1e-3) / 1e12,
             "losses": {"device_run": loss_dev, "e2e_last": {k: float(v) for k, v in logs.items()}}}
-    if not args.no_render and world == 1:
-        try:
-            line["render"] = render_ms_per_frame(precision, dev)
-        except Exception as e:  # the secondary metric must never take the headline down
-            line["render"] = {"error": str(e)[:200]}
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = cpu_train_rays_per_sec()
+    line["render"] = render
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_train_rays_per_sec()      # rank 0's host cores; the other ranks wait
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

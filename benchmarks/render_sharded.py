@@ -60,16 +60,16 @@ def main():
     if st is not None:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     # every rank holds the full frame; it must equal the unsharded render of the same rays and seed.  Checked with
-    # the ordered MMA issue (knerf_debug_tc_variant(3)): the default inference kernel lets its two issuing threads
+    # the ordered MMA issue (KNERF_TC_ORDERED, a per-call option): the default inference kernel lets its two issuing threads
     # interleave, which changes fp32 summation order from run to run, and the reference's out-of-range gather quirk
     #  turns such last-bit differences into visible ones in a handful of pixels.
     from keras_nerf_b200 import _lib
     lib = _lib.load()
-    lib.knerf_debug_tc_variant(3)
+    model._prec_flags |= _lib.TC_ORDERED
     o, d, t = views[(frames - 1) % 2]
     out = model.predict_and_render_images_sharded((o[None], d[None], t[None]), seed=100 + frames - 1)
     ref = model.predict_and_render_images((o[None], d[None], t[None]), seed=100 + frames - 1)
-    lib.knerf_debug_tc_variant(0)
+    model._prec_flags &= ~_lib.TC_ORDERED
     err = float((ref[1]["image"] - out[1]["image"]).abs().max())
     err = max(err, float((ref[0]["depth"] - out[0]["depth"]).abs().max()))
     if rank == 0:

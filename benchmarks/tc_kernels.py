@@ -45,9 +45,9 @@ def main():
         _lib.call("knerf_mlp_forward", C.byref(model.cfg), _lib.ptr(model.fine.params), packed, _lib.ptr(o), _lib.ptr(d),
                   _lib.ptr(t), R, S, prec, train, _lib.ptr(rgbs), ws, wsn, _lib.stream())
 
-    def bwd():
+    def bwd(flags=0):   # flags: _lib.BWD_DGRAD_ONLY / _lib.BWD_WGRAD_ONLY time the two backward kernels apart
         _lib.call("knerf_mlp_backward", C.byref(model.cfg), _lib.ptr(model.fine.params), packed, _lib.ptr(dpre), R, S,
-                  prec, _lib.ptr(grads), ws, wsn, _lib.stream())
+                  prec | flags, _lib.ptr(grads), ws, wsn, _lib.stream())
 
     out = {"rays": R, "samples_per_ray": S, "rows": rows}
 
@@ -57,12 +57,9 @@ def main():
     rec("fwd_infer", _time_ms(lambda: fwd(0), iters), FLOP_FWD_PER_SAMPLE)
     out["fwd_infer"]["tflops_executed"] = round(out["fwd_infer"]["tflops"] * FLOP_FWD_INFER_EXECUTED / FLOP_FWD_PER_SAMPLE, 1)
     rec("fwd_train", _time_ms(lambda: fwd(1), iters), FLOP_FWD_PER_SAMPLE)
-    for name, mask, flop in (("dgrad", 1, FLOP_DGRAD_PER_SAMPLE), ("wgrad", 2, FLOP_WGRAD_PER_SAMPLE)):
-        lib.knerf_debug_backward_parts(mask)
-        try:
-            rec(name, _time_ms(bwd, iters), flop)
-        finally:
-            lib.knerf_debug_backward_parts(3)
+    for name, flag, flop in (("dgrad", _lib.BWD_DGRAD_ONLY, FLOP_DGRAD_PER_SAMPLE),
+                             ("wgrad", _lib.BWD_WGRAD_ONLY, FLOP_WGRAD_PER_SAMPLE)):
+        rec(name, _time_ms(lambda: bwd(flag), iters), flop)
     out["train_ns_per_sample"] = round(sum(out[k]["ns_per_sample"] for k in ("fwd_train", "dgrad", "wgrad")), 4)
     print(json.dumps(out))
 

@@ -12,8 +12,10 @@
  *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it (no host sync).
  *  - Every function returns 0 on success or a negative knerf_status; knerf_last_error() gives the
  *    thread-local message.  No C++ exception crosses the ABI.
- *  - Stateless: no global mutable state; safe to call from several host threads on distinct streams
- *    (the reference calls RaysGenerator from tf.data worker threads, keras_nerf/data/loader.py:96-98).
+ *  - Stateless: no global mutable state and no process-wide mode switches (options travel with each call, see
+ *    KNERF_TC_ORDERED below); safe to call from several host threads on distinct streams (the reference calls
+ *    RaysGenerator from tf.data worker threads, keras_nerf/data/loader.py:96-98).  The only objects the library
+ *    owns are the communicators of knerf_comm_* (multi-GPU), created and destroyed by the caller.
  *  - Randomness is explicit: functions that the reference feeds from tf.random.uniform take the
  *    uniforms as an argument (`u`), or NULL + a seed for the built-in counter-based Philox4x32-10.
  */
@@ -27,14 +29,15 @@
 extern "C" {
 #endif
 
-#define KNERF_ABI_VERSION 1
+#define KNERF_ABI_VERSION 2
 
 typedef enum knerf_status {
   KNERF_OK = 0,
   KNERF_ERR_INVALID = -1,     /* bad argument (null pointer, size, unsupported shape) */
   KNERF_ERR_CUDA = -2,        /* CUDA runtime / launch error */
   KNERF_ERR_UNSUPPORTED = -3, /* configuration outside what the selected precision mode implements */
-  KNERF_ERR_WORKSPACE = -4    /* workspace too small (see knerf_workspace_bytes) */
+  KNERF_ERR_WORKSPACE = -4,   /* workspace too small (see knerf_workspace_bytes) */
+  KNERF_ERR_NCCL = -5         /* NCCL not loadable, or an NCCL call failed (knerf_comm_*, knerf_allreduce_grads) */
 } knerf_status;
 
 /* out-of-range tf.gather in the fine sampler (keras_nerf/model/nerf/utils.py:87-88) */
@@ -56,6 +59,17 @@ typedef enum knerf_precision {
   KNERF_FP32 = 0, /* SIMT FFMA, fp32 end to end: the 1e-5 parity mode                   */
   KNERF_BF16 = 1  /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation         */
 } knerf_precision;
+
+/* Per-call options, OR-ed into every `precision` argument (the library keeps NO process-wide mode switches).
+ *  KNERF_TC_ORDERED     BF16 inference: the two MMA-issuing threads of the forward kernel hand over in ring
+ *                       order like the training kernels do (bit-reproducible outputs, ~14 % slower).  Default:
+ *                       they interleave freely (last-bit run-to-run differences).
+ *  KNERF_BWD_DGRAD_ONLY / KNERF_BWD_WGRAD_ONLY   knerf_mlp_backward (BF16) launches only its dgrad chain kernel /
+ *                       only its weight-gradient kernels, so that a benchmark can time them apart.            */
+#define KNERF_PRECISION_MASK 0xff
+#define KNERF_TC_ORDERED 0x100
+#define KNERF_BWD_DGRAD_ONLY 0x200
+#define KNERF_BWD_WGRAD_ONLY 0x400
 
 /* The 7 ints of model_config.json (keras_nerf/model/nerf/nerf.py:47-55) + encoded widths.
  * dx/dd = width of the xyz / direction encodings fed to the MLP; 0 means 3+6*pos_emb_*.      */
@@ -207,29 +221,41 @@ int knerf_image_metrics(const float* a, const float* b, int B, int H, int W, int
 int knerf_image_prepare(const uint8_t* rgba, int in_h, int in_w, int out_h, int out_w, int white_background,
                         float* out, void* stream);
 
-/* Diagnostic: one tcgen05 tile, D[128,N] (fp32, row-major) = A[128,K] * B[N,K]^T from bf16 operand blobs in
- * the library's chunk-major layout ([K/8][rows][8] for mode 0 = K-major; [rows/8][K][8] for mode 1 =
- * MN-major, the weight-gradient form).  Pins the UMMA descriptor encoding in tests/test_gpu_tc.py.        */
-/* Diagnostic (bench.py roofline): restrict the BF16 knerf_mlp_backward of the calling thread to its dgrad
- * kernel (mask 1), its weight-gradient kernel (mask 2) or both (3, default) so they can be timed apart.  */
-int knerf_debug_backward_parts(int mask);
+/* ---- a14  cross-replica gradient SUM  (train.py:75,110; keras_nerf/model/nerf/nerf.py:455-458) --------------
+ * tf.distribute.MirroredStrategy all-reduces (SUM) every gradient inside optimizer.apply_gradients.  Here: one
+ * process per GPU, one NCCL communicator per process, and the flat fp32 gradient buffers of the two networks
+ * (2 x 595,844 floats) are SUM-all-reduced in place over NVLink.  NCCL is bound at run time
+ * (dlopen("libnccl.so.2"): the copy the host process already loaded, else the system one), so single-GPU users
+ * need no NCCL at all.
+ *   knerf_comm_unique_id    rank 0 fills id_host[KNERF_COMM_ID_BYTES] (HOST memory) and hands the bytes to the other
+ *                           ranks through whatever the host has (MPI, a file, the host framework's own collectives).
+ *   knerf_comm_create       collective over all ranks: builds the communicator for the CURRENT CUDA device.
+ *   knerf_comm_adopt        wraps an existing ncclComm_t of the host framework instead (not destroyed by the library).
+ *   knerf_comm_destroy      frees a communicator (and the NCCL one if knerf_comm_create made it).
+ *   knerf_allreduce_grads   grads[n] (device) <- SUM over ranks, in place, asynchronous on `stream`.
+ * A communicator is used by one host thread at a time (NCCL rule); all ranks issue the same calls in the same order. */
+#define KNERF_COMM_ID_BYTES 128
+typedef struct knerf_comm knerf_comm;
+int knerf_comm_unique_id(void* id_host);
+int knerf_comm_create(const void* id_host, int rank, int nranks, knerf_comm** comm);
+int knerf_comm_adopt(void* nccl_comm, int rank, int nranks, knerf_comm** comm);
+int knerf_comm_destroy(knerf_comm* comm);
+int knerf_comm_rank(const knerf_comm* comm, int* rank, int* nranks);
+int knerf_allreduce_grads(knerf_comm* comm, float* grads, int64_t n, void* stream);
 
-/* Diagnostic: MMA issue order of the BF16 chain kernels.  0 / 2 = default (training kernels issue in ring order
- * and are bit-reproducible; the inference kernel lets its two MMA-issuing threads interleave: last-bit run-to-run
- * differences, 16 % more throughput), 3 = ordered issue at inference too.                                   */
-int knerf_debug_tc_variant(int variant);
-
-/* Diagnostic: per-CTA clock64() counters of the BF16 forward kernel (40 uint64 per CTA; slots documented in
- * csrc/tc_roles.cuh), copied to host_out and cleared.  Returns the number of values written; 0 unless the
- * library was built with -DKNERF_TC_TIMING (release builds carry no instrumentation).                      */
-int knerf_debug_tc_timing(unsigned long long* host_out, int n);
-
-int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
-                        void* stream);
-
-/* Same for one tcgen05.mma.cta_group::2 tile pair: D[256,N] = A[256,K] * B[N,K]^T, a_blob = [2][K/8][128][8],
- * b_blob = [2][K/8][N/2][8] (CTA c of the pair owns A rows 128c.. and B rows c*N/2..).                      */
-int knerf_selftest_umma2(const void* a_blob, const void* b_blob, int N, int K, float* d_out, void* stream);
+/* knerf_train_chunk for ray-sharded data parallelism.  Same arguments and arithmetic; with reduce != 0 (the LAST
+ * accumulation chunk of the step) the all-reduce of grads_coarse (n_params floats) is enqueued on `comm_stream` as
+ * soon as the coarse network's backward has finished -- it travels over NVLink while the fine network is still in
+ * its forward / backward on `stream` -- and the all-reduce of grads_fine follows the fine backward; `stream` waits
+ * for both before the call's work is complete, so an Adam step enqueued on `stream` afterwards sees the reduced
+ * gradients.  comm == NULL or reduce == 0: identical to knerf_train_chunk.  comm_stream must differ from stream.  */
+int knerf_train_chunk_dp(const knerf_config* cfg, const float* params_coarse, const float* params_fine,
+                         const void* packed_coarse, const void* packed_fine, const float* o, const float* d,
+                         const float* t_coarse, const float* target_rgb, int64_t R, const float* u_fine,
+                         uint64_t seed, int white_background, int oob_mode, int precision,
+                         float grad_scale, float* grads_coarse, float* grads_fine, float* losses,
+                         float* image_c, float* image_f, void* workspace, int64_t workspace_bytes,
+                         void* stream, knerf_comm* comm, void* comm_stream, int reduce);
 
 #ifdef __cplusplus
 }

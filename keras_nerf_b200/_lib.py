@@ -18,6 +18,9 @@ LIB_PATH = os.environ.get("KNERF_LIB_PATH") or os.path.join(_HERE, "lib", "libkn
 OOB_ZERO, OOB_CLAMP, OOB_COUNT = 0, 1, 2
 SCAN_SEQUENTIAL = 0x10   # OR-ed into oob_mode: pdf/cdf summed left to right (TF-CPU / NumPy order)
 FP32, BF16 = 0, 1
+# per-call option bits OR-ed into `precision` (include/knerf.h)
+PRECISION_MASK, TC_ORDERED, BWD_DGRAD_ONLY, BWD_WGRAD_ONLY = 0xFF, 0x100, 0x200, 0x400
+COMM_ID_BYTES = 128
 PRECISIONS = {"fp32": FP32, "float32": FP32, "bf16": BF16, "bfloat16": BF16}
 OOB_MODES = {"zero": OOB_ZERO, "clamp": OOB_CLAMP, "raise": OOB_COUNT}
 
@@ -34,7 +37,8 @@ class Config(C.Structure):
 _P, _I, _L, _F, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 _CFG = C.POINTER(Config)
 
-# name -> (restype, argtypes); must list every symbol include/knerf.h declares (tests check this)
+# name -> (restype, argtypes); must list every symbol include/knerf.h and include/knerf_debug.h declare (tests check
+# this)
 SIGNATURES = {
     "knerf_abi_version": (_I, []),
     "knerf_last_error": (C.c_char_p, []),
@@ -64,9 +68,15 @@ SIGNATURES = {
     "knerf_image_prepare": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "knerf_image_metrics_workspace_floats": (_L, [_I, _I, _I, _I]),
     "knerf_image_metrics": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _L, _P]),
-    "knerf_debug_backward_parts": (_I, [_I]),
+    "knerf_comm_unique_id": (_I, [_P]),
+    "knerf_comm_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "knerf_comm_adopt": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "knerf_comm_destroy": (_I, [_P]),
+    "knerf_comm_rank": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "knerf_allreduce_grads": (_I, [_P, _P, _L, _P]),
+    "knerf_train_chunk_dp": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _U64, _I, _I, _I, _F,
+                                  _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I]),
     "knerf_debug_tc_timing": (_I, [_P, _I]),
-    "knerf_debug_tc_variant": (_I, [_I]),
     "knerf_selftest_umma": (_I, [_I, _P, _P, _I, _I, _P, _P]),
     "knerf_selftest_umma2": (_I, [_P, _P, _I, _I, _P, _P]),
 }
@@ -85,7 +95,7 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.knerf_abi_version() != 1:
+        if lib.knerf_abi_version() != 2:
             raise ImportError("libknerf.so ABI version mismatch")
         _lib = lib
     return _lib

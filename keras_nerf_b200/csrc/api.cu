@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "mlp_fp32.cuh"
 #include "mlp_tc.cuh"
+#include "../../include/knerf_debug.h"
 
 #include <atomic>
 
@@ -79,17 +80,6 @@ extern "C" int knerf_device_supports_bf16(void) {
   return (prop.major == 10 && tc_path_compiled()) ? 1 : 0;
 }
 
-extern "C" int knerf_debug_backward_parts(int mask) {
-  tc_set_backward_parts(mask);
-  return KNERF_OK;
-}
-
-extern "C" int knerf_debug_tc_variant(int variant) {
-  KN_CHECK_ARG(variant == 0 || variant == 2 || variant == 3, "knerf_debug_tc_variant: 0 / 2 (default) or 3 (ordered MMA issue)");
-  tc_set_variant(variant);
-  return KNERF_OK;
-}
-
 extern "C" int knerf_debug_tc_timing(unsigned long long* host_out, int n) { return tc_debug_timing(host_out, n); }
 
 extern "C" int64_t knerf_param_count(const knerf_config* cfg) {
@@ -115,6 +105,7 @@ extern "C" int64_t knerf_workspace_bytes(const knerf_config* cfg, int64_t rows, 
   Model m;
   if (build_model(cfg, &m) != KNERF_OK || rows < 0) return -1;
   int64_t mlp = 0;
+  precision &= KNERF_PRECISION_MASK;
   if (precision == KNERF_FP32) mlp = (int64_t)make_fp32_plan(m, rows, training != 0).total;
   else if (precision == KNERF_BF16) mlp = tc_workspace_bytes(m, rows, training != 0);
   else return -1;

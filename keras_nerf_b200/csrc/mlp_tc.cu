@@ -474,15 +474,6 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
 bool tc_path_compiled() { return true; }
 
-// knerf_debug_tc_variant(3): the two MMA-issuing threads keep ring order at inference too (bit-reproducible
-// outputs; training kernels always do).  0 / 2: default.
-static int g_tc_variant = 0;
-void tc_set_variant(int v) { g_tc_variant = v; }
-bool tc_ordered_issue() {
-  static const bool env = std::getenv("KNERF_TC_ORDERED") != nullptr;   // same switch from the environment
-  return g_tc_variant == 3 || env;
-}
-
 // diagnostic (-DKNERF_TC_TIMING builds only): copy and clear the forward kernel's per-CTA cycle counters
 int tc_debug_timing(unsigned long long* host_out, int n) {
 #ifdef KNERF_TC_TIMING
@@ -522,7 +513,8 @@ int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStrea
 }
 
 int tc_forward(const Model& m, const float* params, const void* packed, const float* o, const float* d, const float* t,
-               int64_t R, int S, bool training, float* rgbsigma, char* ws, int64_t ws_bytes, cudaStream_t st) {
+               int64_t R, int S, bool training, bool ordered_issue, float* rgbsigma, char* ws, int64_t ws_bytes,
+               cudaStream_t st) {
   (void)params;
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
   const int64_t M = R * S;
@@ -544,9 +536,9 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // MMA issue order (tc_roles2.cuh): bit-reproducible when training, free-running at inference unless
-  // knerf_debug_tc_variant(3) asks for the ordered form
-  const int ordered = (training || tc_ordered_issue()) ? 1 : 0;
+  // MMA issue order (tc_roles2.cuh): bit-reproducible when training, free-running at inference unless the call
+  // carries KNERF_TC_ORDERED
+  const int ordered = (training || ordered_issue) ? 1 : 0;
   const uint8_t* pk = (const uint8_t*)packed;
   float4* out = (float4*)rgbsigma;
   uint8_t* rec = training ? (uint8_t*)ws + kXBytes : nullptr;

@@ -577,13 +577,9 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
 
 }  // namespace
 
-// diagnostic: which of the backward kernels knerf_mlp_backward launches in BF16 mode (bit 0 dgrad, bit 1 wgrad +
-// finish)
-static thread_local int g_bwd_parts = 3;
-void tc_set_backward_parts(int mask) { g_bwd_parts = mask & 3; }
-
+// parts: which of the backward kernels to launch (bit 0 dgrad, bit 1 wgrad + finish; KNERF_BWD_*_ONLY)
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
-                float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
+                float* grads, char* ws, int64_t ws_bytes, int parts, cudaStream_t st) {
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
@@ -597,7 +593,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   uint8_t* dz = rec + n_tiles * (int64_t)kRecBytes;
   const TcParams P = tc_make_params(m);
 
-  if (g_bwd_parts & 1) {
+  if (parts & 1) {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     cfg.blockDim = dim3(kThreads);
@@ -615,7 +611,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel, pk, dp, M, rec_c, dz, grads, P));
     KN_LAUNCH_CHECK();
   }
-  if (g_bwd_parts & 2) {
+  if (parts & 2) {
     static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
     // items ~ 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 170 -> 217 + 36 + 41 = 294 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));

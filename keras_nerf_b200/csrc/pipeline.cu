@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "mlp_fp32.cuh"
 #include "mlp_tc.cuh"
+#include "comm.cuh"
 
 namespace knerf {
 int launch_sum_scale(const float* x, int64_t n, float scale, float* out, int accumulate, cudaStream_t st);
@@ -33,10 +34,12 @@ static int carve(void* ws, int64_t bytes, int64_t R, int S, bool training, Chunk
   return KNERF_OK;
 }
 
+// `precision` carries the per-call option bits of knerf.h (KNERF_TC_ORDERED, KNERF_BWD_*_ONLY)
 static int mlp_forward_impl(const Model& m, const float* params, const void* packed, const float* o, const float* d,
-                            const float* t, int64_t R, int S, int precision, bool training, float* rgbsigma,
+                            const float* t, int64_t R, int S, int precision_flags, bool training, float* rgbsigma,
                             char* ws, int64_t ws_bytes, cudaStream_t st) {
   const int64_t rows = R * S;
+  const int precision = precision_flags & KNERF_PRECISION_MASK;
   if (precision == KNERF_FP32) {
     const Fp32Plan p = make_fp32_plan(m, rows, training);
     if ((int64_t)p.total > ws_bytes)
@@ -50,14 +53,16 @@ static int mlp_forward_impl(const Model& m, const float* params, const void* pac
   }
   if (precision == KNERF_BF16) {
     if (packed == nullptr) return fail(KNERF_ERR_INVALID, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
-    return tc_forward(m, params, packed, o, d, t, R, S, training, rgbsigma, ws, ws_bytes, st);
+    return tc_forward(m, params, packed, o, d, t, R, S, training, (precision_flags & KNERF_TC_ORDERED) != 0, rgbsigma,
+                      ws, ws_bytes, st);
   }
   return fail(KNERF_ERR_INVALID, "unknown precision %d", precision);
 }
 
 static int mlp_backward_impl(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R,
-                             int S, int precision, float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
+                             int S, int precision_flags, float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
   const int64_t rows = R * S;
+  const int precision = precision_flags & KNERF_PRECISION_MASK;
   if (precision == KNERF_FP32) {
     const Fp32Plan p = make_fp32_plan(m, rows, true);
     if ((int64_t)p.total > ws_bytes)
@@ -66,7 +71,10 @@ static int mlp_backward_impl(const Model& m, const float* params, const void* pa
     return fp32_backward_core(m, params, (const float*)(ws + p.off_x0), p.ldx, (const float*)(ws + p.off_dir), p.ldd,
                               d_pre, rows, ws, p, grads, st);
   }
-  if (precision == KNERF_BF16) return tc_backward(m, params, packed, d_pre, R, S, grads, ws, ws_bytes, st);
+  if (precision == KNERF_BF16) {
+    const int parts = (precision_flags & KNERF_BWD_DGRAD_ONLY) ? 1 : (precision_flags & KNERF_BWD_WGRAD_ONLY) ? 2 : 3;
+    return tc_backward(m, params, packed, d_pre, R, S, grads, ws, ws_bytes, parts, st);
+  }
   return fail(KNERF_ERR_INVALID, "unknown precision %d", precision);
 }
 
@@ -84,7 +92,11 @@ using namespace knerf;
 extern "C" int64_t knerf_packed_weight_bytes(const knerf_config* cfg) {
   Model m;
   if (build_model(cfg, &m) != KNERF_OK) return -1;
-  return tc_packed_weight_bytes(m);
+  const int64_t n = tc_packed_weight_bytes(m);
+  if (n < 0)
+    fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only (got %d x %d, skip %d, L=%d,%d)",
+         m.n_layers, m.U, m.cfg.skip_layer, m.cfg.pos_emb_xyz, m.cfg.pos_emb_dir);
+  return n;
 }
 
 extern "C" int knerf_pack_weights(const knerf_config* cfg, const float* params, void* packed, void* stream) {
@@ -148,12 +160,15 @@ extern "C" int knerf_render_chunk(const knerf_config* cfg, const float* params_c
   return KNERF_OK;
 }
 
-extern "C" int knerf_train_chunk(const knerf_config* cfg, const float* params_coarse, const float* params_fine,
-                                 const void* packed_coarse, const void* packed_fine, const float* o, const float* d,
-                                 const float* t_coarse, const float* target_rgb, int64_t R, const float* u_fine,
-                                 uint64_t seed, int white_background, int oob_mode, int precision, float grad_scale,
-                                 float* grads_coarse, float* grads_fine, float* losses, float* image_c,
-                                 float* image_f, void* workspace, int64_t workspace_bytes, void* stream) {
+// one chunk of train_step; comm != nullptr: the all-reduce of each network's accumulated gradient is enqueued on
+// comm_stream right behind that network's backward (knerf_train_chunk_dp)
+static int train_chunk_impl(const knerf_config* cfg, const float* params_coarse, const float* params_fine,
+                            const void* packed_coarse, const void* packed_fine, const float* o, const float* d,
+                            const float* t_coarse, const float* target_rgb, int64_t R, const float* u_fine,
+                            uint64_t seed, int white_background, int oob_mode, int precision, float grad_scale,
+                            float* grads_coarse, float* grads_fine, float* losses, float* image_c, float* image_f,
+                            void* workspace, int64_t workspace_bytes, void* stream, knerf_comm* comm,
+                            void* comm_stream) {
   Model m;
   KN_TRY(check_model_for_rays(cfg, &m));
   KN_CHECK_ARG(params_coarse && params_fine && o && d && t_coarse && target_rgb && grads_coarse && grads_fine &&
@@ -177,6 +192,8 @@ extern "C" int knerf_train_chunk(const knerf_config* cfg, const float* params_co
   KN_TRY(launch_sum_scale(c.sqerr, R, mse_scale, losses, 1, st));
   KN_TRY(mlp_backward_impl(m, params_coarse, packed_coarse, c.d_pre, R, Nc, precision, grads_coarse, c.mlp,
                            c.mlp_bytes, st));
+  // the coarse gradient is final: it crosses NVLink while the fine network runs
+  if (comm != nullptr) KN_TRY(comm_allreduce_after(comm, grads_coarse, m.n_params, st, (cudaStream_t)comm_stream, 0));
   // ---- fine network; coarse weights are constants, no gradient through the sampler (nerf.py:390-417) ----
   KN_TRY(knerf_sample_fine(t_coarse, nullptr, c.weights, u_fine, seed, nullptr, R, Nc, Nf, oob_mode, c.t_sorted,
                            nullptr, nullptr, nullptr, nullptr, st));
@@ -189,5 +206,35 @@ extern "C" int knerf_train_chunk(const knerf_config* cfg, const float* params_co
                                   loss_scale, 1, c.d_pre, c.sqerr, st));
   KN_TRY(launch_sum_scale(c.sqerr, R, mse_scale, losses + 1, 1, st));
   KN_TRY(mlp_backward_impl(m, params_fine, packed_fine, c.d_pre, R, S, precision, grads_fine, c.mlp, c.mlp_bytes, st));
+  if (comm != nullptr) {
+    KN_TRY(comm_allreduce_after(comm, grads_fine, m.n_params, st, (cudaStream_t)comm_stream, 1));
+    KN_TRY(comm_join(comm, (cudaStream_t)comm_stream, st));   // `stream` continues once both reductions are done
+  }
   return KNERF_OK;
+}
+
+extern "C" int knerf_train_chunk(const knerf_config* cfg, const float* params_coarse, const float* params_fine,
+                                 const void* packed_coarse, const void* packed_fine, const float* o, const float* d,
+                                 const float* t_coarse, const float* target_rgb, int64_t R, const float* u_fine,
+                                 uint64_t seed, int white_background, int oob_mode, int precision, float grad_scale,
+                                 float* grads_coarse, float* grads_fine, float* losses, float* image_c,
+                                 float* image_f, void* workspace, int64_t workspace_bytes, void* stream) {
+  return train_chunk_impl(cfg, params_coarse, params_fine, packed_coarse, packed_fine, o, d, t_coarse, target_rgb, R,
+                          u_fine, seed, white_background, oob_mode, precision, grad_scale, grads_coarse, grads_fine,
+                          losses, image_c, image_f, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int knerf_train_chunk_dp(const knerf_config* cfg, const float* params_coarse, const float* params_fine,
+                                    const void* packed_coarse, const void* packed_fine, const float* o, const float* d,
+                                    const float* t_coarse, const float* target_rgb, int64_t R, const float* u_fine,
+                                    uint64_t seed, int white_background, int oob_mode, int precision,
+                                    float grad_scale, float* grads_coarse, float* grads_fine, float* losses,
+                                    float* image_c, float* image_f, void* workspace, int64_t workspace_bytes,
+                                    void* stream, knerf_comm* comm, void* comm_stream, int reduce) {
+  const bool dp = comm != nullptr && reduce != 0;
+  if (dp) KN_CHECK_ARG(comm_stream != stream, "knerf_train_chunk_dp: comm_stream must differ from stream");
+  return train_chunk_impl(cfg, params_coarse, params_fine, packed_coarse, packed_fine, o, d, t_coarse, target_rgb, R,
+                          u_fine, seed, white_background, oob_mode, precision, grad_scale, grads_coarse, grads_fine,
+                          losses, image_c, image_f, workspace, workspace_bytes, stream, dp ? comm : nullptr,
+                          dp ? comm_stream : nullptr);
 }

@@ -3,8 +3,14 @@
 One process per GPU (torchrun).  Rays are independent units, so the data path has NO collective; the only
 exchange is the SUM all-reduce of the flat accumulated MLP gradient (2 x 595,844 fp32 = 4.77 MB) that
 MirroredStrategy performs inside `apply_gradients` (nerf.py:455-458; SUM, not mean: train.py:134-136), and a
-gather of rendered pixels for inference.  torch.distributed is the plumbing (NCCL over NVLink on GPUs, gloo
-for the CPU tests of the host logic)."""
+gather of rendered pixels for inference.
+
+The gradient all-reduce of the training step lives behind the C ABI: `knerf_comm()` builds a libknerf
+communicator (its own NCCL communicator, bootstrapped by broadcasting the 128-byte unique id over
+torch.distributed) and `NeRF.accumulate_gradients` hands it to `knerf_train_chunk_dp`, which issues the coarse
+network's all-reduce on a side stream while the fine network is still in its backward.  torch.distributed is the
+rendezvous / bootstrap plumbing and carries the rest (parameter broadcast, pixel gather, metric means; gloo for
+the CPU tests of the host logic, where the gradient SUM falls back to `dist.all_reduce`)."""
 from __future__ import annotations
 
 import contextlib
@@ -32,7 +38,11 @@ class RayShardedStrategy:
                 dist.init_process_group(backend)
         self.rank = dist.get_rank()
         self.num_replicas_in_sync = dist.get_world_size()
-        self.device = device
+        if device is None and dist.get_backend() == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())   # NCCL rejects CPU tensors
+        self.device = torch.device(device) if device is not None else None
+        self._comm = None            # libknerf communicator (knerf_comm*), created on first use
+        self._comm_stream = None
 
     @contextlib.contextmanager
     def scope(self):  # API parity with `with strategy.scope():` (train.py:110)
@@ -58,10 +68,46 @@ class RayShardedStrategy:
         return x.narrow(dim, lo, hi - lo)
 
     # ---- collectives ---------------------------------------------------------------------------
+    def knerf_comm(self):
+        """(knerf_comm*, cudaStream_t) for knerf_train_chunk_dp / knerf_allreduce_grads, or (None, None) when there
+        is nothing to reduce or no GPU (gloo tests).  Collective on first use: every rank must call it."""
+        if self.num_replicas_in_sync == 1 or self.device is None or self.device.type != "cuda":
+            return None, None
+        if self._comm is None:
+            import ctypes as C
+            from . import _lib
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                ident = (C.c_ubyte * _lib.COMM_ID_BYTES)()
+                if self.rank == 0:
+                    _lib.check(lib.knerf_comm_unique_id(ident))
+                dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+                t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+                dist.broadcast(t, src=0)
+                ident = (C.c_ubyte * _lib.COMM_ID_BYTES)(*t.cpu().tolist())
+                comm = C.c_void_p()
+                _lib.check(lib.knerf_comm_create(ident, self.rank, self.num_replicas_in_sync, C.byref(comm)))
+                self._comm = comm
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+        return self._comm, self._comm_stream.cuda_stream
+
+    def close(self):
+        if self._comm is not None:
+            from . import _lib
+            _lib.load().knerf_comm_destroy(self._comm)
+            self._comm = None
+
     def all_reduce_sum(self, *tensors):
         if self.num_replicas_in_sync == 1:
             return
-        # the two accumulators are views of one flat buffer when allocated by NeRF: one collective
+        comm, _ = self.knerf_comm()
+        if comm is not None and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in tensors):
+            from . import _lib
+            with torch.cuda.device(self.device):
+                for t in tensors:        # behind the C ABI, on the caller's current stream
+                    _lib.call("knerf_allreduce_grads", comm, t.data_ptr(), t.numel(), _lib.stream())
+            return
+        # CPU / gloo: the two accumulators are views of one flat buffer when allocated by NeRF: one collective
         if len(tensors) == 2 and tensors[0].untyped_storage().data_ptr() == tensors[1].untyped_storage().data_ptr():
             base = tensors[0]._base if tensors[0]._base is not None else tensors[0]
             dist.all_reduce(base, op=dist.ReduceOp.SUM)

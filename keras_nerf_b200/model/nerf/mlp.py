@@ -19,12 +19,42 @@ def set_seed(seed: int) -> None:
     _init_rng = np.random.default_rng(seed)
 
 
+def _truncated_normal(rng, stddev, shape):
+    """Keras' VarianceScaling(distribution='truncated_normal'): samples within two standard deviations, the
+    standard deviation corrected by 0.87962566103423978 so that the truncated distribution has the asked variance"""
+    sd = stddev / 0.87962566103423978
+    out = rng.normal(0.0, sd, size=shape)
+    bad = np.abs(out) > 2 * sd
+    while bad.any():
+        out[bad] = rng.normal(0.0, sd, size=int(bad.sum()))
+        bad = np.abs(out) > 2 * sd
+    return out
+
+
+# Keras initializer identifiers accepted by Dense(kernel_initializer=...) (keras_nerf/model/nerf/mlp.py:5,13-27):
+# name -> f(rng, fan_in, fan_out) -> [fan_in, fan_out] float64
+INITIALIZERS = {
+    "glorot_uniform": lambda r, fi, fo: r.uniform(-math.sqrt(6.0 / (fi + fo)), math.sqrt(6.0 / (fi + fo)), (fi, fo)),
+    "glorot_normal": lambda r, fi, fo: _truncated_normal(r, math.sqrt(2.0 / (fi + fo)), (fi, fo)),
+    "he_uniform": lambda r, fi, fo: r.uniform(-math.sqrt(6.0 / fi), math.sqrt(6.0 / fi), (fi, fo)),
+    "he_normal": lambda r, fi, fo: _truncated_normal(r, math.sqrt(2.0 / fi), (fi, fo)),
+    "lecun_uniform": lambda r, fi, fo: r.uniform(-math.sqrt(3.0 / fi), math.sqrt(3.0 / fi), (fi, fo)),
+    "lecun_normal": lambda r, fi, fo: _truncated_normal(r, math.sqrt(1.0 / fi), (fi, fo)),
+    "random_uniform": lambda r, fi, fo: r.uniform(-0.05, 0.05, (fi, fo)),
+    "random_normal": lambda r, fi, fo: r.normal(0.0, 0.05, (fi, fo)),
+    "zeros": lambda r, fi, fo: np.zeros((fi, fo)),
+    "ones": lambda r, fi, fo: np.ones((fi, fo)),
+}
+
+
 class NeRFMLP:
     def __init__(self, n_layers: int = 8, dense_units: int = 256, skip_layer=4, initializer='glorot_uniform',
                  name=None, device=None, **kwargs):
         # keras_nerf/model/nerf/mlp.py:5-27
-        if initializer != 'glorot_uniform':
-            raise NotImplementedError("only Keras' default glorot_uniform initializer is implemented")
+        if not callable(initializer) and str(initializer).lower() not in INITIALIZERS:
+            raise NotImplementedError(f"initializer {initializer!r}: one of {sorted(INITIALIZERS)} or a callable "
+                                      "f(rng, fan_in, fan_out) -> [fan_in, fan_out] array")
+        self.initializer = initializer
         self.n_layers = int(n_layers)
         self.dense_units = int(dense_units)
         self.skip_layer = int(skip_layer)
@@ -56,9 +86,9 @@ class NeRFMLP:
             raise _lib.KnerfError(lib.knerf_last_error().decode())
         self.layers = [(int(k_off[i]), int(b_off[i]), int(fin[i]), int(fout[i])) for i in range(nl)]
         host = np.zeros(n, dtype=np.float32)
-        for ko, bo, fi, fo in self.layers:
-            lim = math.sqrt(6.0 / (fi + fo))
-            host[ko:ko + fi * fo] = _init_rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32).reshape(-1)
+        init = self.initializer if callable(self.initializer) else INITIALIZERS[str(self.initializer).lower()]
+        for ko, bo, fi, fo in self.layers:    # kernels in Keras variable order; biases stay zero (Dense default)
+            host[ko:ko + fi * fo] = np.asarray(init(_init_rng, fi, fo)).astype(np.float32).reshape(-1)
         self.params = torch.from_numpy(host).to(self.device)
         return self
 

@@ -6,9 +6,12 @@ Differences that are visible to a caller (all additive):
   * `precision` ("fp32" = SIMT parity mode, "bf16" = tcgen05 tensor-core mode) and `oob_mode`
     ("zero" = TF-GPU gather semantics, the parity default) constructor keywords;
   * `u_fine=` keywords expose the uniform draws the reference takes from tf.random.uniform;
-  * data parallelism = one process per GPU; pass `strategy=RayShardedStrategy()` (or just initialise
-    torch.distributed) and the accumulated gradients are SUM-all-reduced over NCCL before Adam, which is
-    what tf.distribute.MirroredStrategy does inside apply_gradients (train.py:75,110; nerf.py:455-458).
+  * data parallelism = one process per GPU; pass `strategy=RayShardedStrategy()` -- or just initialise
+    torch.distributed with more than one rank before constructing the model, in which case a strategy is created
+    automatically -- and the accumulated gradients are SUM-all-reduced over NCCL (inside libknerf,
+    `knerf_train_chunk_dp`: the coarse network's gradient travels while the fine network is still in its
+    backward) before Adam, which is what tf.distribute.MirroredStrategy does inside apply_gradients
+    (train.py:75,110; nerf.py:455-458).
 """
 from __future__ import annotations
 
@@ -98,7 +101,15 @@ def image_metrics(a: torch.Tensor, b: torch.Tensor, max_val: float = 1.0):
     return out
 
 
-_seed_counter = itertools.count(0xC0A45E00)
+def _seed_base():
+    """Philox seed stream of this process for draws the caller did not pin (`seed=None`): keyed by the torch seed
+    (torch.manual_seed / tf.random.set_seed in the scripts) and by the RANK, so the replicas of a data-parallel run
+    draw independent fine samples (every replica of a MirroredStrategy gets its own tf.random stream too)."""
+    rank = int(os.environ.get("RANK", "0"))
+    return (0xC0A45E00 + (torch.initial_seed() & 0xFFFFFFFF) * 0x9E3779B1 + rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+
+
+_seed_counter = itertools.count(_seed_base())
 
 
 class NeRF:
@@ -121,14 +132,16 @@ class NeRF:
         # fp32 parity mode sums the pdf/cdf in TF-CPU order (bit-identical cdf); bf16 mode uses the warp scan
         self.scan_mode = scan_mode or ("sequential" if precision in ("fp32", "float32") else "warp")
         self.device = torch.device(device) if device is not None else None
+        if strategy is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            from ...distributed import RayShardedStrategy
+            strategy = RayShardedStrategy(device=self.device)        # replicas must not train unsynchronised
         self.strategy = strategy
         # bf16 inference: the forward kernel's two MMA-issuing threads interleave freely by default (last-bit
         # run-to-run differences, which the out-of-range gather quirk of the fine sampler can amplify in single
         # pixels); reproducible=True makes them hand over in order like the training kernels (-14 % throughput).
-        # Process-wide switch of the library (knerf_debug_tc_variant).
+        # A per-call option of the library (KNERF_TC_ORDERED), i.e. per model: other models are unaffected.
         self.reproducible = bool(reproducible)
-        if self.reproducible:
-            _lib.load().knerf_debug_tc_variant(3)
         self.coarse = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
                               name='coarse_nerf', device=device)
         self.fine = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
@@ -151,8 +164,8 @@ class NeRF:
 
     @staticmethod
     def has_checkpoint(path) -> bool:
-        """the existence check of the scripts (train_single.py:91-92, inference.py:51-54): `coarse.h5` + `fine.h5`,
-        which this package stores as `.npz` archives with the Keras variable names"""
+        """the existence check of the scripts (train_single.py:91-92, inference.py:51-54): `coarse.h5` + `fine.h5`
+        in Keras' legacy HDF5 weight layout (utils/hdf5.py); `.npz` archives of an early version are still found"""
         return all(any(os.path.exists(os.path.join(path, n + ext)) for ext in ('.npz', '.h5'))
                    for n in ('coarse', 'fine'))
 
@@ -168,9 +181,15 @@ class NeRF:
                 is_training=True, **kwargs):
         self.run_eagerly = bool(kwargs.get("run_eagerly", False))
         self.optimizer, self.loss = optimizer, loss
-        lname = (loss if isinstance(loss, str) else getattr(loss, "name", type(loss).__name__)).lower()
-        if "mean_squared" not in lname and "mse" not in lname and "meansquared" not in lname and not callable(loss):
-            raise NotImplementedError("only the mean-squared-error loss of the reference scripts is implemented")
+        # The fused kernels implement the loss of the reference scripts: MeanSquaredError (train_single.py:127) or
+        # train.py:130-136's `compute_distributed_loss` wrapper around it (accepted by name, or by the explicit
+        # `knerf_loss = "mse"` attribute on a callable).  Anything else would be silently replaced: refuse it.
+        lname = (loss if isinstance(loss, str) else
+                 getattr(loss, "knerf_loss", None) or getattr(loss, "name", None) or getattr(loss, "__name__", None)
+                 or type(loss).__name__).lower()
+        if not any(k in lname for k in ("mean_squared", "meansquared", "mse", "compute_distributed_loss")):
+            raise NotImplementedError(f"loss {loss!r}: only the mean-squared-error loss of the reference scripts is "
+                                      "implemented (tag an equivalent callable with `knerf_loss = 'mse'`)")
         self.batch_size, self.image_height, self.image_width = batch_size, image_height, image_width
         self.white_background = white_background
         self.ray_chunks = ray_chunks
@@ -209,8 +228,14 @@ class NeRF:
             lib = _lib.load()
             nbytes = lib.knerf_packed_weight_bytes(C.byref(self.cfg))
             if nbytes <= 0:
-                raise _lib.KnerfError("bf16 (tcgen05) mode is not available for this configuration / build: "
-                                      + lib.knerf_last_error().decode())
+                # the tcgen05 chain kernels implement the 8x256 / skip 4 / L = 10,4 model of the reference's defaults;
+                # any other shape its CLI accepts (--num_units, --num_layers, --skip_layer, --pos_emb_*) runs in the
+                # fp32 SIMT mode -- loudly
+                logging.warning("precision='bf16' is not available for this model shape (%s); using the fp32 mode",
+                                lib.knerf_last_error().decode() or "unsupported configuration")
+                self.precision, self._prec = "fp32", _lib.FP32
+        self._prec_flags = self._prec | (_lib.TC_ORDERED if self.reproducible else 0)
+        if self._prec == _lib.BF16:
             for name in ("coarse", "fine"):
                 self._packed[name] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._repack()
@@ -275,7 +300,7 @@ class NeRF:
             _lib.call("knerf_render_chunk", C.byref(self.cfg), _lib.ptr(self.coarse.params), _lib.ptr(self.fine.params),
                       self._packed_ptr("coarse"), self._packed_ptr("fine"), _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R,
                       _lib.ptr(u_fine), int(seed), int(bool(self.white_background)),
-                      self._sampler_flags(), self._prec,
+                      self._sampler_flags(), self._prec_flags,
                       _lib.ptr(outs_c[0]), _lib.ptr(outs_c[1]), _lib.ptr(outs_c[2]),
                       _lib.ptr(outs_f[0]), _lib.ptr(outs_f[1]), _lib.ptr(outs_f[2]), _lib.ptr(t_sorted),
                       self._ws.data_ptr(), self._ws.numel(), _lib.stream())
@@ -362,9 +387,10 @@ class NeRF:
         return {m.name: m.result() for m in self.metrics}
 
     # ---- training (nerf.py:332-473) -----------------------------------------------------------
-    def accumulate_gradients(self, images, rays, u_fine=None, seed=None, want_images=True):
+    def accumulate_gradients(self, images, rays, u_fine=None, seed=None, want_images=True, reduce=True):
         """The chunk loop of train_step (nerf.py:351-421): fills the two gradient accumulators and the loss
-        accumulators; returns (coarse_images, fine_images) [B,H,W,3] (or None)."""
+        accumulators; returns (coarse_images, fine_images) [B,H,W,3] (or None).  With a multi-rank strategy and
+        reduce=True the accumulators hold the cross-replica SUM when the enqueued work completes."""
         images = _lib.dev(images, self.device)[..., :3]                           # nerf.py:335
         n = self.num_rays
         target = images.reshape(n, 3).contiguous()
@@ -375,18 +401,21 @@ class NeRF:
         seed = next(_seed_counter) if seed is None else seed
         rc, nch = self.ray_chunks, self.sequential_chunks
         oob = self._sampler_flags()
+        # data parallel: the all-reduce rides inside the LAST chunk's call (coarse half behind the coarse backward)
+        comm, comm_stream = (None, None) if self.strategy is None or not reduce else self.strategy.knerf_comm()
+        self._grads_reduced = comm is not None
         with torch.cuda.device(self.device):
             for i in range(nch):
                 s = slice(i * rc, (i + 1) * rc)
-                _lib.call("knerf_train_chunk", C.byref(self.cfg), _lib.ptr(self.coarse.params),
+                _lib.call("knerf_train_chunk_dp", C.byref(self.cfg), _lib.ptr(self.coarse.params),
                           _lib.ptr(self.fine.params), self._packed_ptr("coarse"), self._packed_ptr("fine"),
                           _lib.ptr(o[s]), _lib.ptr(d[s]), _lib.ptr(t[s]), _lib.ptr(target[s]), rc,
-                          None if u is None else _lib.ptr(u[s]), int(seed + i * 0x9E3779B1),
-                          int(bool(self.white_background)), oob, self._prec, 1.0 / nch,
+                          None if u is None else _lib.ptr(u[s]), int(seed + i * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF,
+                          int(bool(self.white_background)), oob, self._prec_flags, 1.0 / nch,
                           _lib.ptr(self.coarse_gradients_accumulator), _lib.ptr(self.fine_gradients_accumulator),
                           _lib.ptr(self._losses), None if ci is None else _lib.ptr(ci[s]),
                           None if fi is None else _lib.ptr(fi[s]), self._ws.data_ptr(), self._ws.numel(),
-                          _lib.stream())
+                          _lib.stream(), comm, comm_stream, int(comm is not None and i == nch - 1))
         B, H, W = self.batch_size, self.image_height, self.image_width
         if not want_images:
             return None, None
@@ -394,8 +423,9 @@ class NeRF:
 
     def apply_gradients(self):
         """nerf.py:455-471: cross-replica SUM (MirroredStrategy semantics), two Adam steps, zero accumulators."""
-        if self.strategy is not None:
+        if self.strategy is not None and not getattr(self, "_grads_reduced", False):
             self.strategy.all_reduce_sum(self.coarse_gradients_accumulator, self.fine_gradients_accumulator)
+        self._grads_reduced = False
         with torch.cuda.device(self.device):
             self.coarse_optimizer.apply_flat(self.coarse.params, self.coarse_gradients_accumulator, zero_grads=True)
             self.fine_optimizer.apply_flat(self.fine.params, self.fine_gradients_accumulator, zero_grads=True)

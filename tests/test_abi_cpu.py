@@ -21,14 +21,14 @@ def lib():
 
 
 def test_header_symbols_exported(lib):
-    header = open(os.path.join(ROOT, "include", "knerf.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("knerf.h", "knerf_debug.h"))
     declared = set(re.findall(r"\b(knerf_[a-z0-9_]+)\s*\(", header))
     assert len(declared) >= 20
     raw = C.CDLL(lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in knerf.h but not exported"
     assert declared == set(lib.SIGNATURES), "ctypes table out of sync with knerf.h"
-    assert lib.load().knerf_abi_version() == 1
+    assert lib.load().knerf_abi_version() == 2
 
 
 def test_no_torch_types_in_abi():

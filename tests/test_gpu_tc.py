@@ -69,12 +69,12 @@ def _rays(R, S, seed=0):
     return o.to(dev), d.to(dev), t.to(dev), tgt.to(dev)
 
 
-def _fwd(m, net, o, d, t, training):
+def _fwd(m, net, o, d, t, training, flags=0):
     from keras_nerf_b200 import _lib
     R, S = t.shape
     out = torch.full((R, S, 4), float("nan"), device=t.device)
     _lib.call("knerf_mlp_forward", C.byref(m.cfg), _lib.ptr(net.params), m._packed_ptr("fine" if net is m.fine else "coarse"),
-              _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R, S, m._prec, int(training), _lib.ptr(out), m._ws.data_ptr(),
+              _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), R, S, m._prec | flags, int(training), _lib.ptr(out), m._ws.data_ptr(),
               m._ws.numel(), _lib.stream())
     return out
 
@@ -228,17 +228,17 @@ def test_tc_training_kernels_are_bit_reproducible(R, S):
     """The chain kernels have TWO MMA-issuing threads (tc_roles2.cuh).  When training they hand over in ring order,
     so the fp32 accumulation order is fixed: forward output, activation / ReLU' records and the dZ records are
     bit-identical run after run; weight gradients differ only by the order of the fp32 atomics.  At inference the
-    issuers run free by default (last-bit differences allowed) and knerf_debug_tc_variant(3) restores the order."""
+    issuers run free by default (last-bit differences allowed) and the per-call option KNERF_TC_ORDERED restores the
+    order -- for that call only: the library keeps no mode switch."""
     from keras_nerf_b200 import _lib
     lib = _lib.load()
     _, m = _models(R)
     o, d, t, tgt = _rays(R, S, seed=11 + R)
     res = []
-    try:
-        lib.knerf_debug_tc_variant(3)
+    if True:
         for run in range(2):
             m._ws.zero_()
-            inf = _fwd(m, m.fine, o, d, t, False)
+            inf = _fwd(m, m.fine, o, d, t, False, flags=_lib.TC_ORDERED)
             out = _fwd(m, m.fine, o, d, t, True)
             dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
             _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
@@ -249,8 +249,6 @@ def test_tc_training_kernels_are_bit_reproducible(R, S):
             nbytes = int(lib.knerf_workspace_bytes(C.byref(m.cfg), R * S, m._prec, 1))
             # skip the fp32 X scratch at the head of the workspace (atomics)
             res.append((out.clone(), inf.clone(), m._ws.view(torch.uint8)[256 * 1024:nbytes].clone(), gbuf.clone()))
-    finally:
-        lib.knerf_debug_tc_variant(0)
     a, b = res
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])            # training / ordered inference forward
     assert torch.equal(a[0], a[1])                                        # saving records does not change the output
