@@ -507,13 +507,24 @@ def test_model_train_two_steps_golden():
                         float(g[f"s{step}_grad_{name}_abssum"][k]), rel=5e-4 if tight else 5e-2, abs=1e-9)
                     off += n
                     k += 1
+        gmax_c = float(np.abs(g[f"s{step}_grad_coarse_head"]).max())
         model.apply_gradients()
         assert float(model.coarse_gradients_accumulator.abs().max()) == 0.0     # nerf.py:465-471
+        checked = 0
         for name, net in (("coarse", model.coarse), ("fine", model.fine)):
             for k, v in enumerate(net.trainable_variables):
                 m = min(v.numel(), 32)
-                np.testing.assert_allclose(v.reshape(-1)[:m].cpu().numpy(), g[f"s{step}_param_{name}_head"][k][:m],
-                                           atol=2.1e-3)
+                got, want = v.reshape(-1)[:m].cpu().numpy(), g[f"s{step}_param_{name}_head"][k][:m]
+                # Adam's first steps move every weight by ~lr * sign(g): where the gradient is ~0 the sign is noise,
+                # so 2 * lr is all that can be said there ...
+                np.testing.assert_allclose(got, want, atol=2.1e-3)
+                # ... but where the reference's gradient is clearly non-zero (coarse network, first step: the
+                # gradients themselves agree to 5e-5 * max) the update must be the reference's, to 1e-5
+                if name == "coarse" and step == 0:
+                    sel = np.abs(g[f"s{step}_grad_{name}_head"][k][:m]) > 1e-2 * gmax_c
+                    checked += int(sel.sum())
+                    np.testing.assert_allclose(got[sel], want[sel], atol=1e-5)
+        assert step > 0 or checked >= 50
 
 
 def test_train_step_metrics_and_oracle():
