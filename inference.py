@@ -28,7 +28,7 @@ def main(argv=None):
     parser.add_argument('--output_dir', type=str, default='output')
     parser.add_argument('--output_freq', type=int, default=10)
     parser.add_argument('--verbose', action='store_true')
-    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_tc'])
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO,
                         format='%(asctime)s | %(name)s | %(levelname)s | %(message)s')

@@ -106,7 +106,8 @@ extern "C" int64_t knerf_workspace_bytes(const knerf_config* cfg, int64_t rows, 
   if (build_model(cfg, &m) != KNERF_OK || rows < 0) return -1;
   int64_t mlp = 0;
   precision &= KNERF_PRECISION_MASK;
-  if (precision == KNERF_FP32) mlp = (int64_t)make_fp32_plan(m, rows, training != 0).total;
+  if (precision == KNERF_FP32 || precision == KNERF_FP32_TC)
+    mlp = (int64_t)make_fp32_plan(m, rows, training != 0, precision == KNERF_FP32_TC).total;
   else if (precision == KNERF_BF16) mlp = tc_workspace_bytes(m, rows, training != 0);
   else return -1;
   if (mlp < 0) return -1;

@@ -17,15 +17,6 @@ namespace knerf {
 // ---------------------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBN = 128, GBK = 8, GPAD = 4;
 
-enum Epilogue { EPI_NONE = 0, EPI_RELU = 1, EPI_SIGMOID = 2, EPI_MASK = 3 };
-
-struct GemmArgs {
-  const float* A1; int lda1; int K1; const float* B1; int ldb1;
-  const float* A2; int lda2; int K2; const float* B2; int ldb2;
-  const float* bias; float* C; int ldc; int64_t M; int N; int epi;
-  const float* mask; int ldmask;   // EPI_MASK: C = acc * (mask > 0)
-};
-
 template <bool TRANS_B>
 __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
@@ -133,8 +124,72 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   }
 }
 
-static int launch_gemm(const GemmArgs& g, bool trans_b, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------------
+// Heads with 1..4 outputs (sigma: N = 1, rgb: N = 3): C[M,N] = epi(A1 B1 + A2 B2 + bias) is a bandwidth problem (it
+// reads every activation row once), which the 128-wide tiles above turn into a compute one.  One warp per row: the
+// lanes stride over the reduction, N <= 4 partial sums each, butterfly reduction in a fixed order.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(GemmArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < g.M; row += warps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int src = 0; src < 2; ++src) {
+      const float* A = src ? g.A2 : g.A1;
+      const float* B = src ? g.B2 : g.B1;
+      const int lda = src ? g.lda2 : g.lda1, ldb = src ? g.ldb2 : g.ldb1, K = (A == nullptr) ? 0 : (src ? g.K2 : g.K1);
+      for (int k = lane; k < K; k += 32) {
+        const float a = A[row * lda + k];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+          if (n < g.N) acc[n] = fmaf(a, __ldg(B + (int64_t)k * ldb + n), acc[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[n] = warp_sum(acc[n]);
+    if (lane < g.N) {
+      float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      if (g.bias != nullptr) v += g.bias[lane];
+      if (g.epi == EPI_RELU) v = fmaxf(v, 0.f);
+      else if (g.epi == EPI_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+      g.C[row * g.ldc + lane] = v;
+    }
+  }
+}
+
+// dW[K,N] += A[M,K]^T Z[M,N] for N <= 4: thread k of a block owns row k of dW, the block walks a slab of samples
+// (A rows read coalesced, the Z row broadcast), one red.global.add per element and slab
+__global__ void __launch_bounds__(256)
+skinny_wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __restrict__ Z, int ldz, int N, int64_t M,
+                    int64_t slab, float* __restrict__ dW, int ldw) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int64_t mb = (int64_t)blockIdx.y * slab, me = min(mb + slab, M);
+  if (k >= K) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = mb; r < me; ++r) {
+    const float a = A[r * lda + k];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < N) acc[n] = fmaf(a, __ldg(Z + r * ldz + n), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+    if (n < N) atomicAdd(&dW[(int64_t)k * ldw + n], acc[n]);
+}
+
+// blob1 / blob2: split weight operands of the two sources (KNERF_FP32_TC) -- when given and the shape qualifies, the
+// GEMM runs on the tensor cores (mlp_fp32_tc.cu); otherwise SIMT
+static int launch_gemm(const GemmArgs& g, bool trans_b, cudaStream_t st, const void* blob1 = nullptr,
+                       const void* blob2 = nullptr) {
   if (g.M == 0 || g.N == 0) return KNERF_OK;
+  if (!trans_b && g.N <= 4 && g.epi != EPI_MASK) {
+    skinny_gemm_kernel<<<(unsigned)std::min<int64_t>(cdiv(g.M, 8), (int64_t)kNumSMs * 16), 256, 0, st>>>(g);
+    KN_LAUNCH_CHECK();
+    return KNERF_OK;
+  }
+  if ((blob1 != nullptr || g.K1 == 0 || g.A1 == nullptr) && (blob2 != nullptr || g.K2 == 0 || g.A2 == nullptr) &&
+      (blob1 != nullptr || blob2 != nullptr) && tcx_gemm_eligible(g))
+    return launch_gemm_tc(g, blob1, blob2, st);
   dim3 grid((unsigned)cdiv(g.M, GBM), (unsigned)cdiv(g.N, GBN));
   if (trans_b) sgemm_kernel<true><<<grid, 256, 0, st>>>(g);
   else sgemm_kernel<false><<<grid, 256, 0, st>>>(g);
@@ -196,8 +251,18 @@ wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __restric
 }
 
 static int launch_wgrad(const float* A, int lda, int K, const float* Z, int ldz, int N, int64_t M, float* dW,
-                        int ldw, cudaStream_t st) {
+                        int ldw, cudaStream_t st, bool tc = false) {
   if (M == 0 || K == 0 || N == 0) return KNERF_OK;
+  if (N <= 4) {
+    const int kb = (int)cdiv(K, 256);
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(M, 64), cdiv((int64_t)kNumSMs * 8, kb)));
+    const int64_t slab = cdiv(M, splits);
+    splits = cdiv(M, slab);
+    skinny_wgrad_kernel<<<dim3((unsigned)kb, (unsigned)splits), 256, 0, st>>>(A, lda, K, Z, ldz, N, M, slab, dW, ldw);
+    KN_LAUNCH_CHECK();
+    return KNERF_OK;
+  }
+  if (tc && tcx_wgrad_eligible(K, N)) return launch_wgrad_tc(A, lda, K, Z, ldz, N, M, dW, ldw, st);
   const int tiles = (int)(cdiv(K, WBK) * cdiv(N, WBN));
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(M, 4 * WBM), cdiv((int64_t)kNumSMs * 8, tiles)));
   int64_t slab = align_up(cdiv(M, splits), WBM);
@@ -243,9 +308,10 @@ static int launch_colsum(const float* Z, int ldz, int N, int64_t M, float* db, c
 // ---------------------------------------------------------------------------------------------------
 // workspace plan
 // ---------------------------------------------------------------------------------------------------
-Fp32Plan make_fp32_plan(const Model& m, int64_t rows, bool training) {
+Fp32Plan make_fp32_plan(const Model& m, int64_t rows, bool training, bool tc) {
   Fp32Plan p{};
   p.rows = rows;
+  p.tc = tc;
   p.ldx = (m.dx + 3) & ~3;
   p.ldd = (m.dd + 3) & ~3;
   size_t off = 0;
@@ -263,6 +329,14 @@ Fp32Plan make_fp32_plan(const Model& m, int64_t rows, bool training) {
     p.off_d1 = take((size_t)rows * m.U);
     p.off_dg = take((size_t)rows * (m.U / 2));
   }
+  if (tc) {
+    for (int i = 0; i < m.n_dense; ++i) {
+      const LayerDesc& L = m.L[i];
+      p.off_fwd1[i] = take(tcx_blob_bytes(L.fan_out, L.k_h) / 4 + 1);
+      p.off_fwd2[i] = take(tcx_blob_bytes(L.fan_out, L.k_x) / 4 + 1);
+      p.off_bwd[i] = training ? take(tcx_blob_bytes(L.k_h, L.fan_out) / 4 + 1) : 0;
+    }
+  }
   p.total = off;
   return p;
 }
@@ -271,10 +345,36 @@ Fp32Plan make_fp32_plan(const Model& m, int64_t rows, bool training) {
 // forward: hidden stack + heads.  X0/DIR are the encoded inputs (any leading dims).
 // out_rgb/out_sigma: ld 3/1 (separate, NeRFMLP.call) or both into a packed [rows,4] buffer (ld 4).
 // ---------------------------------------------------------------------------------------------------
+static bool tc_width(int n) { return n >= 64 && n <= 256 && n % 64 == 0; }
+// operand blobs of layer i (nullptr: SIMT)
+static const void* fwd_blob1(const Model& m, const Fp32Plan& p, const char* ws, int i) {
+  return (p.tc && tc_width(m.L[i].fan_out) && m.L[i].k_h > 0) ? ws + p.off_fwd1[i] : nullptr;
+}
+static const void* fwd_blob2(const Model& m, const Fp32Plan& p, const char* ws, int i) {
+  return (p.tc && tc_width(m.L[i].fan_out) && m.L[i].k_x > 0) ? ws + p.off_fwd2[i] : nullptr;
+}
+static const void* bwd_blob(const Model& m, const Fp32Plan& p, const char* ws, int i) {
+  return (p.tc && tc_width(m.L[i].k_h)) ? ws + p.off_bwd[i] : nullptr;
+}
+
+// KNERF_FP32_TC: split every kernel into its bf16 x 3 operand blobs (forward form; dgrad form too when training)
+static int tc_pack_all(const Model& m, const float* params, char* ws, const Fp32Plan& p, bool training, cudaStream_t st) {
+  for (int i = 0; i < m.n_dense; ++i) {
+    const LayerDesc& L = m.L[i];
+    const float* W = params + L.w_off;
+    if (fwd_blob1(m, p, ws, i)) KN_TRY(tcx_pack(W, L.fan_out, L.fan_out, L.k_h, false, ws + p.off_fwd1[i], st));
+    if (fwd_blob2(m, p, ws, i))
+      KN_TRY(tcx_pack(W + (int64_t)L.k_h * L.fan_out, L.fan_out, L.fan_out, L.k_x, false, ws + p.off_fwd2[i], st));
+    if (training && bwd_blob(m, p, ws, i)) KN_TRY(tcx_pack(W, L.fan_out, L.k_h, L.fan_out, true, ws + p.off_bwd[i], st));
+  }
+  return KNERF_OK;
+}
+
 int fp32_forward_core(const Model& m, const float* params, const float* X0, int ldx, const float* DIR, int ldd,
                       int64_t rows, char* ws, const Fp32Plan& p, float* out_rgb, int ld_rgb, float* out_sigma,
-                      int ld_sigma, cudaStream_t st) {
+                      int ld_sigma, cudaStream_t st, bool training) {
   const int n = m.n_layers, U = m.U;
+  if (p.tc) KN_TRY(tc_pack_all(m, params, ws, p, training, st));
   auto H = [&](int i) { return reinterpret_cast<float*>(ws + p.off_h[i]); };
   float* F = reinterpret_cast<float*>(ws + p.off_f);
   float* G = reinterpret_cast<float*>(ws + p.off_g);
@@ -284,7 +384,7 @@ int fp32_forward_core(const Model& m, const float* params, const float* X0, int 
     g.A1 = (i == 0) ? nullptr : H(i - 1); g.lda1 = U; g.K1 = L.k_h; g.B1 = params + L.w_off; g.ldb1 = L.fan_out;
     g.A2 = X0; g.lda2 = ldx; g.K2 = L.k_x; g.B2 = params + L.w_off + (int64_t)L.k_h * L.fan_out; g.ldb2 = L.fan_out;
     g.bias = params + L.b_off; g.C = H(i); g.ldc = U; g.M = rows; g.N = L.fan_out; g.epi = EPI_RELU;   // mlp.py:33-34
-    KN_TRY(launch_gemm(g, false, st));
+    KN_TRY(launch_gemm(g, false, st, fwd_blob1(m, p, ws, i), fwd_blob2(m, p, ws, i)));
   }
   const float* Hl = H(n - 1);
   {  // sigma = relu(h @ Ws + bs)   (mlp.py:40)
@@ -301,7 +401,7 @@ int fp32_forward_core(const Model& m, const float* params, const float* X0, int 
     g.A1 = Hl; g.lda1 = U; g.K1 = L.k_h; g.B1 = params + L.w_off; g.ldb1 = L.fan_out;
     g.A2 = X0; g.lda2 = ldx; g.K2 = L.k_x; g.B2 = params + L.w_off + (int64_t)L.k_h * L.fan_out; g.ldb2 = L.fan_out;
     g.bias = params + L.b_off; g.C = F; g.ldc = U; g.M = rows; g.N = L.fan_out; g.epi = EPI_NONE;
-    KN_TRY(launch_gemm(g, false, st));
+    KN_TRY(launch_gemm(g, false, st, fwd_blob1(m, p, ws, n + 1), fwd_blob2(m, p, ws, n + 1)));
   }
   {  // rgb_features = [features, dir] @ Wg + bg   (linear, no activation: mlp.py:43-46)
     const LayerDesc& L = m.L[n + 2];
@@ -309,7 +409,7 @@ int fp32_forward_core(const Model& m, const float* params, const float* X0, int 
     g.A1 = F; g.lda1 = U; g.K1 = L.k_h; g.B1 = params + L.w_off; g.ldb1 = L.fan_out;
     g.A2 = DIR; g.lda2 = ldd; g.K2 = L.k_x; g.B2 = params + L.w_off + (int64_t)L.k_h * L.fan_out; g.ldb2 = L.fan_out;
     g.bias = params + L.b_off; g.C = G; g.ldc = U / 2; g.M = rows; g.N = L.fan_out; g.epi = EPI_NONE;
-    KN_TRY(launch_gemm(g, false, st));
+    KN_TRY(launch_gemm(g, false, st, fwd_blob1(m, p, ws, n + 2), fwd_blob2(m, p, ws, n + 2)));
   }
   {  // rgb = sigmoid(g @ Wc + bc)   (mlp.py:48)
     const LayerDesc& L = m.L[n + 3];
@@ -339,7 +439,7 @@ int fp32_backward_core(const Model& m, const float* params, const float* X0, int
   const LayerDesc &Ls = m.L[n], &Lf = m.L[n + 1], &Lg = m.L[n + 2], &Lc = m.L[n + 3];
 
   // rgb layer: dWc += G^T d_rgbpre ; dbc ; dG = d_rgbpre @ Wc^T
-  KN_TRY(launch_wgrad(G, U2, U2, d_pre, 4, 3, rows, grads + Lc.w_off, 3, st));
+  KN_TRY(launch_wgrad(G, U2, U2, d_pre, 4, 3, rows, grads + Lc.w_off, 3, st, p.tc));
   KN_TRY(launch_colsum(d_pre, 4, 3, rows, grads + Lc.b_off, st));
   {
     GemmArgs g{};
@@ -348,41 +448,41 @@ int fp32_backward_core(const Model& m, const float* params, const float* X0, int
     KN_TRY(launch_gemm(g, true, st));
   }
   // rgb_features (linear): dWg[:U] += F^T dG ; dWg[U:] += DIR^T dG ; dbg ; dF = dG @ Wg[:U]^T
-  KN_TRY(launch_wgrad(F, U, Lg.k_h, DG, U2, U2, rows, grads + Lg.w_off, U2, st));
-  KN_TRY(launch_wgrad(DIR, ldd, Lg.k_x, DG, U2, U2, rows, grads + Lg.w_off + (int64_t)Lg.k_h * U2, U2, st));
+  KN_TRY(launch_wgrad(F, U, Lg.k_h, DG, U2, U2, rows, grads + Lg.w_off, U2, st, p.tc));
+  KN_TRY(launch_wgrad(DIR, ldd, Lg.k_x, DG, U2, U2, rows, grads + Lg.w_off + (int64_t)Lg.k_h * U2, U2, st, p.tc));
   KN_TRY(launch_colsum(DG, U2, U2, rows, grads + Lg.b_off, st));
   {
     GemmArgs g{};
     g.A1 = DG; g.lda1 = U2; g.K1 = U2; g.B1 = params + Lg.w_off; g.ldb1 = U2; g.K2 = 0;
     g.C = D0; g.ldc = U; g.M = rows; g.N = U; g.epi = EPI_NONE;
-    KN_TRY(launch_gemm(g, true, st));
+    KN_TRY(launch_gemm(g, true, st, bwd_blob(m, p, ws, n + 2), nullptr));
   }
   // features (linear) + sigma head share the input h_last (and x after a trailing skip)
-  KN_TRY(launch_wgrad(Hl, U, Lf.k_h, D0, U, U, rows, grads + Lf.w_off, U, st));
-  KN_TRY(launch_wgrad(X0, ldx, Lf.k_x, D0, U, U, rows, grads + Lf.w_off + (int64_t)Lf.k_h * U, U, st));
+  KN_TRY(launch_wgrad(Hl, U, Lf.k_h, D0, U, U, rows, grads + Lf.w_off, U, st, p.tc));
+  KN_TRY(launch_wgrad(X0, ldx, Lf.k_x, D0, U, U, rows, grads + Lf.w_off + (int64_t)Lf.k_h * U, U, st, p.tc));
   KN_TRY(launch_colsum(D0, U, U, rows, grads + Lf.b_off, st));
-  KN_TRY(launch_wgrad(Hl, U, Ls.k_h, d_pre + 3, 4, 1, rows, grads + Ls.w_off, 1, st));
-  KN_TRY(launch_wgrad(X0, ldx, Ls.k_x, d_pre + 3, 4, 1, rows, grads + Ls.w_off + Ls.k_h, 1, st));
+  KN_TRY(launch_wgrad(Hl, U, Ls.k_h, d_pre + 3, 4, 1, rows, grads + Ls.w_off, 1, st, p.tc));
+  KN_TRY(launch_wgrad(X0, ldx, Ls.k_x, d_pre + 3, 4, 1, rows, grads + Ls.w_off + Ls.k_h, 1, st, p.tc));
   KN_TRY(launch_colsum(d_pre + 3, 4, 1, rows, grads + Ls.b_off, st));
   {  // dZ_{n-1} = (dF @ Wf[:U]^T + d_sigmapre @ Ws[:U]^T) * (h_last > 0)
     GemmArgs g{};
     g.A1 = D0; g.lda1 = U; g.K1 = U; g.B1 = params + Lf.w_off; g.ldb1 = U;
     g.A2 = d_pre + 3; g.lda2 = 4; g.K2 = 1; g.B2 = params + Ls.w_off; g.ldb2 = 1;
     g.C = D1; g.ldc = U; g.M = rows; g.N = U; g.epi = EPI_MASK; g.mask = Hl; g.ldmask = U;
-    KN_TRY(launch_gemm(g, true, st));
+    KN_TRY(launch_gemm(g, true, st, bwd_blob(m, p, ws, n + 1), bwd_blob(m, p, ws, n)));
   }
   float* dz = D1;
   float* other = D0;
   for (int i = n - 1; i >= 0; --i) {
     const LayerDesc& L = m.L[i];
-    if (i > 0) KN_TRY(launch_wgrad(H(i - 1), U, L.k_h, dz, U, U, rows, grads + L.w_off, U, st));
-    KN_TRY(launch_wgrad(X0, ldx, L.k_x, dz, U, U, rows, grads + L.w_off + (int64_t)L.k_h * U, U, st));
+    if (i > 0) KN_TRY(launch_wgrad(H(i - 1), U, L.k_h, dz, U, U, rows, grads + L.w_off, U, st, p.tc));
+    KN_TRY(launch_wgrad(X0, ldx, L.k_x, dz, U, U, rows, grads + L.w_off + (int64_t)L.k_h * U, U, st, p.tc));
     KN_TRY(launch_colsum(dz, U, U, rows, grads + L.b_off, st));
     if (i > 0) {  // dZ_{i-1} = (dZ_i @ W_i[:U]^T) * (h_{i-1} > 0)   (no gradient into the x / dir inputs)
       GemmArgs g{};
       g.A1 = dz; g.lda1 = U; g.K1 = U; g.B1 = params + L.w_off; g.ldb1 = U; g.K2 = 0;
       g.C = other; g.ldc = U; g.M = rows; g.N = L.k_h; g.epi = EPI_MASK; g.mask = H(i - 1); g.ldmask = U;
-      KN_TRY(launch_gemm(g, true, st));
+      KN_TRY(launch_gemm(g, true, st, bwd_blob(m, p, ws, i), nullptr));
       std::swap(dz, other);
     }
   }

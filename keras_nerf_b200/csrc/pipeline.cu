@@ -40,8 +40,8 @@ static int mlp_forward_impl(const Model& m, const float* params, const void* pac
                             char* ws, int64_t ws_bytes, cudaStream_t st) {
   const int64_t rows = R * S;
   const int precision = precision_flags & KNERF_PRECISION_MASK;
-  if (precision == KNERF_FP32) {
-    const Fp32Plan p = make_fp32_plan(m, rows, training);
+  if (precision == KNERF_FP32 || precision == KNERF_FP32_TC) {
+    const Fp32Plan p = make_fp32_plan(m, rows, training, precision == KNERF_FP32_TC);
     if ((int64_t)p.total > ws_bytes)
       return fail(KNERF_ERR_WORKSPACE, "knerf_mlp_forward: workspace %lld < %lld bytes", (long long)ws_bytes,
                   (long long)p.total);
@@ -49,7 +49,7 @@ static int mlp_forward_impl(const Model& m, const float* params, const void* pac
     float* DIR = (float*)(ws + p.off_dir);
     KN_TRY(knerf_encode_position_and_directions(o, d, t, R, S, m.cfg.pos_emb_xyz, m.cfg.pos_emb_dir, X0, p.ldx, DIR,
                                                 p.ldd, st));
-    return fp32_forward_core(m, params, X0, p.ldx, DIR, p.ldd, rows, ws, p, rgbsigma, 4, rgbsigma + 3, 4, st);
+    return fp32_forward_core(m, params, X0, p.ldx, DIR, p.ldd, rows, ws, p, rgbsigma, 4, rgbsigma + 3, 4, st, training);
   }
   if (precision == KNERF_BF16) {
     if (packed == nullptr) return fail(KNERF_ERR_INVALID, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
@@ -63,8 +63,8 @@ static int mlp_backward_impl(const Model& m, const float* params, const void* pa
                              int S, int precision_flags, float* grads, char* ws, int64_t ws_bytes, cudaStream_t st) {
   const int64_t rows = R * S;
   const int precision = precision_flags & KNERF_PRECISION_MASK;
-  if (precision == KNERF_FP32) {
-    const Fp32Plan p = make_fp32_plan(m, rows, true);
+  if (precision == KNERF_FP32 || precision == KNERF_FP32_TC) {
+    const Fp32Plan p = make_fp32_plan(m, rows, true, precision == KNERF_FP32_TC);
     if ((int64_t)p.total > ws_bytes)
       return fail(KNERF_ERR_WORKSPACE, "knerf_mlp_backward: workspace %lld < %lld bytes", (long long)ws_bytes,
                   (long long)p.total);

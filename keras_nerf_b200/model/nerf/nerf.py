@@ -3,7 +3,8 @@ test_step / predict_and_render_images / save_model / load_model signatures, runn
 
 Differences that are visible to a caller (all additive):
   * tensors are torch CUDA tensors (numpy / CPU tensors are accepted as inputs);
-  * `precision` ("fp32" = SIMT parity mode, "bf16" = tcgen05 tensor-core mode) and `oob_mode`
+  * `precision` ("fp32" = SIMT parity mode, "fp32_tc" = the same fp32-grade arithmetic on the tensor cores through
+    3-way bf16 operand splitting, "bf16" = tcgen05 throughput mode) and `oob_mode`
     ("zero" = TF-GPU gather semantics, the parity default) constructor keywords;
   * `u_fine=` keywords expose the uniform draws the reference takes from tf.random.uniform;
   * data parallelism = one process per GPU; pass `strategy=RayShardedStrategy()` -- or just initialise
@@ -130,7 +131,7 @@ class NeRF:
         self.precision = precision
         self.oob_mode = oob_mode
         # fp32 parity mode sums the pdf/cdf in TF-CPU order (bit-identical cdf); bf16 mode uses the warp scan
-        self.scan_mode = scan_mode or ("sequential" if precision in ("fp32", "float32") else "warp")
+        self.scan_mode = scan_mode or ("warp" if precision in ("bf16", "bfloat16") else "sequential")
         self.device = torch.device(device) if device is not None else None
         if strategy is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
@@ -441,6 +442,17 @@ class NeRF:
             for name, g in (("Coarse", self.coarse_gradients_accumulator), ("Fine", self.fine_gradients_accumulator)):
                 if not bool(torch.isfinite(g).all()):
                     raise FloatingPointError(f"{name} Gradient is not finite")
+        if self.run_eagerly:
+            # nerf.py:429-451 (eager-only diagnostics): a network whose gradient is identically zero has stopped
+            # learning -- typically a dead sigma head
+            nz_c = int(torch.count_nonzero(self.coarse_gradients_accumulator))
+            nz_f = int(torch.count_nonzero(self.fine_gradients_accumulator))
+            if nz_c == 0 and nz_f == 0:
+                logging.error('Both Coarse and Fine Gradient are zero')
+            elif nz_c == 0:
+                logging.warning('Coarse Gradient is zero')
+            elif nz_f == 0:
+                logging.warning('Fine Gradient is zero')
         self.apply_gradients()
         imgs = _lib.dev(images, self.device)[..., :3]
         lc, lf = losses.tolist()

@@ -174,7 +174,9 @@ def test_config0_render_and_train_step_vs_oracle_on_a_subsample_of_chunks():
     torch.cuda.synchronize()
     want = torch.stack(per_chunk).double().mean(0)
     got = m._grad_flat.double()
-    assert float((got - want.to(got.device)).abs().max()) <= 1e-6 * float(want.abs().max()) + 1e-12
+    # (fp32 atomics inside every chunk's weight-gradient kernels: 2e-5 of the largest entry, as in
+    # test_gpu_parity.py::test_config2_4096_ray_step_properties)
+    assert float((got - want.to(got.device)).abs().max()) <= 2e-5 * float(want.abs().max())
 
 
 # ---- bf16 tolerance on trained weights ----------------------------------------------------------------------------

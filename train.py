@@ -66,7 +66,7 @@ def main(argv=None, multi_gpu=True):
     parser.add_argument('--log_dir', type=str, default='logs')
     parser.add_argument('--log_freq', type=int, default=5 if multi_gpu else 1)
     parser.add_argument('--verbose', action='store_true')
-    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_tc'])
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO,
                         format='%(asctime)s | %(name)s | %(levelname)s | %(message)s')
