@@ -106,12 +106,15 @@ def dominant_kernel_roofline(model, precision, peaks):
         add("tc_mlp_dgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_DGRAD_ONLY)), FLOP_DGRAD_PER_SAMPLE, BYTES_DGRAD, 1)
         add("tc_wgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_WGRAD_ONLY)), FLOP_WGRAD_PER_SAMPLE, BYTES_WGRAD, 2)
     else:
-        add("fp32 forward (13 launches: encode + 12 sgemm_kernel)", ms_f, FLOP_FWD_PER_SAMPLE, None, n_f)
+        tag = ("fp32_tc forward (encode + tcx_pack + tcx_gemm_kernel + skinny heads)" if precision == "fp32_tc"
+               else "fp32 forward (encode + sgemm_kernel + skinny heads)")
+        add(tag, ms_f, FLOP_FWD_PER_SAMPLE, None, n_f)
         l0 = lib.knerf_launch_count()
         bwd()
         n_b = int(lib.knerf_launch_count() - l0)
-        add("fp32 backward (sgemm_kernel<T> + wgrad_kernel + colsum_kernel)", _time_ms(bwd),
-            FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE, None, n_b)
+        tag = ("fp32_tc backward (tcx_gemm_kernel + tcx_wgrad_kernel + colsum_kernel)" if precision == "fp32_tc"
+               else "fp32 backward (sgemm_kernel<T> + wgrad_kernel + colsum_kernel)")
+        add(tag, _time_ms(bwd), FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE, None, n_b)
 
     name = max(kernels, key=lambda k: kernels[k]["ms"])   # the dominant kernel = the one the step spends most time in
     k = kernels[name]
@@ -124,7 +127,10 @@ def dominant_kernel_roofline(model, precision, peaks):
                                if per_sample else None),
             "design_bytes_hbm_frac": k.get("design_bytes_hbm_frac"),
             "samples_per_launch": rows, "peak_source": src, "kernels": kernels}
-    if precision != "bf16":
+    if precision == "fp32_tc":
+        roof["note"] = ("fp32-grade mode on the tensor cores: every product is six bf16 MMAs, so 1/6 of the bf16 peak "
+                        "(270 TFLOP/s burst) is its ceiling; TFLOP/s count the fp32 work once")
+    elif precision != "bf16":
         roof["note"] = "fp32 SIMT FFMA parity mode measured against the bf16 tensor peak"
     return roof
 

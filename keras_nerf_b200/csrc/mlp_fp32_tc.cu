@@ -22,7 +22,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int kXThreads = 320;          // warps 0-7 compute (split + epilogue), warp 8 = MMA issue, warp 9 = bulk copies
+constexpr int kXThreads = 320;          // weight-gradient kernel: warps 0-7 compute (split + flush), warps 8 and 9 = MMA
+                                        // issue (feature rows 0..127 / 128..255: one issuer per accumulator)
 // the six products, ordered from the smallest terms to the largest (the order only matters for rounding)
 __device__ __constant__ int8_t kProdA[6] = {2, 1, 0, 1, 0, 0};
 __device__ __constant__ int8_t kProdB[6] = {0, 1, 2, 0, 1, 0};
@@ -43,13 +44,36 @@ __device__ __forceinline__ void split3x8(const float (&x)[8], uint4& p1, uint4& 
   p3 = make_uint4(w3[0], w3[1], w3[2], w3[3]);
 }
 
+// 4 consecutive fp32 -> three 8-byte vectors of bf16 (x1 | x2 | x3)
+__device__ __forceinline__ void split3x4(const float4 x, uint2& p1, uint2& p2, uint2& p3) {
+  const uint32_t a1 = pack_bf16x2(x.x, x.y), b1 = pack_bf16x2(x.z, x.w);
+  const float r0 = x.x - bf16_lo(a1), r1 = x.y - bf16_hi(a1), r2 = x.z - bf16_lo(b1), r3 = x.w - bf16_hi(b1);   // exact
+  const uint32_t a2 = pack_bf16x2(r0, r1), b2 = pack_bf16x2(r2, r3);
+  p1 = make_uint2(a1, b1);
+  p2 = make_uint2(a2, b2);
+  p3 = make_uint2(pack_bf16x2(r0 - bf16_lo(a2), r1 - bf16_hi(a2)), pack_bf16x2(r2 - bf16_lo(b2), r3 - bf16_hi(b2)));
+}
+
+// 4 fp32 of row `grow`, reduction columns k0 .. k0 + 3 of source A (zero beyond M / K)
+__device__ __forceinline__ float4 load_a4(const float* __restrict__ A, int lda, int K, int64_t grow, int64_t M, int k0) {
+  if (grow < M && k0 + 4 <= K && (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0)
+    return __ldg(reinterpret_cast<const float4*>(A + grow * lda + k0));
+  float x[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) x[e] = (grow < M && k0 + e < K) ? __ldg(A + grow * lda + k0 + e) : 0.f;
+  return make_float4(x[0], x[1], x[2], x[3]);
+}
+
 // ---- weight operand blobs -------------------------------------------------------------------------------------
 // B[n][k] (n < N outputs, k < K reduction) = src[k * ld + n] (TRANS = false: a Keras kernel [in,out] used forward) or
-// src[n * ld + k] (TRANS = true: the same kernel used by dgrad).  Blob: [K16 steps][3 splits][2 chunks][N][8] bf16,
-// zero beyond K.  One thread per 16-byte vector of split 0 (writes the same vector of all three splits).
+// src[n * ld + k] (TRANS = true: the same kernel used by dgrad).  The GEMM kernel works on column blocks of NU outputs
+// (NU = N for N <= 128, N / 2 above); blob: [N / NU blocks][K16 steps][3 splits][2 chunks][NU][8] bf16, zero beyond K, so
+// that one (block, step) stage is ONE contiguous bulk copy.  One thread per 16-byte vector (all three splits).
+__host__ __device__ inline int tcx_nu(int N) { return N; }   // column block of a work unit: all of N (tcx_gemm_kernel)
+
 __global__ void __launch_bounds__(256) tcx_pack_kernel(const float* __restrict__ src, int ld, int N, int K, int trans,
                                                        uint8_t* __restrict__ blob) {
-  const int ksteps = (K + 15) / 16;
+  const int ksteps = (K + 15) / 16, NU = tcx_nu(N);
   const int total = ksteps * 2 * N;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
     const int n = v % N, c = (v / N) & 1, ks = v / (2 * N);
@@ -61,23 +85,36 @@ __global__ void __launch_bounds__(256) tcx_pack_kernel(const float* __restrict__
     }
     uint4 p1, p2, p3;
     split3x8(x, p1, p2, p3);
-    uint8_t* base = blob + (size_t)ks * 96 * N + (size_t)(c * N + n) * 16;
+    const int nb = n / NU, nl = n - nb * NU;
+    uint8_t* base = blob + ((size_t)nb * ksteps + ks) * 96 * NU + (size_t)(c * NU + nl) * 16;
     *reinterpret_cast<uint4*>(base) = p1;
-    *reinterpret_cast<uint4*>(base + 32 * N) = p2;
-    *reinterpret_cast<uint4*>(base + 64 * N) = p3;
+    *reinterpret_cast<uint4*>(base + 32 * NU) = p2;
+    *reinterpret_cast<uint4*>(base + 64 * NU) = p3;
   }
 }
 
 // ---- C = epi(A1 B1 + A2 B2 + bias) ----------------------------------------------------------------------------
-// One CTA per SM takes 256 rows = TWO 128-row tiles that share every weight stage: the split weights are 6 bytes per
-// element, and with one tile per stage the bulk copies alone (384 KB per tile and layer) sat at the ~42 B/clk an SM
-// can ingest from L2 (measured: 36 % of the MMA-bound time with 128-row CTAs, two per SM).
+// Persistent CTAs (one per SM).  A work unit is 256 rows = two 128-row tiles that share every weight stage, times ALL
+// N <= 256 output columns: the two fp32 accumulators fill the TMEM.  Warp roles: 0-7 load the fp32 rows and split
+// them (three K = 16 steps in flight per thread), 8 and 14 issue the MMAs (one tile each), 9 streams the split weights
+// with bulk copies, 10-13 are the epilogue (bias from shared memory, ReLU / ReLU' mask, fp32 rows to HBM) -- while
+// they drain a unit the loads, splits and bulk copies of the next one already fill the stage ring.
+// What the measurements said (profiles/r02_fp32_tc.md): the kernel is bound by its LOAD / STORE PATH, not by the
+// tensor pipe -- removing every MMA but one changed the time by 5 %, removing the A loads by 34 %, the C stores by
+// 19 %.  Hence: A is read once per unit (column-block units re-read it: slower although their epilogue overlapped
+// the next unit's MMAs), a load instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16, the bias
+// comes from shared memory (per-element global loads were 37 % of all stall samples), and 128-row CTAs (two per SM)
+// lost to the 6-byte-per-element weight stream they each had to re-fetch.
+constexpr int kGThreads = 480;          // warps 0-7 split A, 8 and 14 = MMA issue (tile 0 / tile 1), 9 = bulk copies,
+                                        // 10-13 = epilogue
 constexpr int kGStages = 4;
 struct GemmSmem {
-  // per stage: A [2 tiles][3 splits][2 chunks][128 rows][8] = 24 KB, B [3][2][N <= 256][8] = 24 KB
+  // per stage: A [2 tiles][3 splits][2 chunks][128 rows][8] = 24 KB, B [3][2][NU <= 256][8] = 24 KB
   uint8_t a[kGStages][2 * 3 * 4096];
   uint8_t b[kGStages][3 * 8192];
-  uint64_t full[kGStages], a_ready[kGStages], empty[kGStages], acc_ready;
+  float bias[256];                      // staged once: a scalar global load per column and row sat on the epilogue's
+                                        // critical path (ncu: 37 % of all stall samples on the dependent FADDs)
+  uint64_t full[kGStages], a_ready[kGStages], empty[kGStages], acc_ready[2], acc_free[2];
   uint32_t tmem_base;
 };
 
@@ -88,148 +125,174 @@ struct XGemmArgs {
   const float* mask; int ldmask;
 };
 
-// 8 fp32 of row `grow`, reduction columns k0 .. k0 + 7 of source A (zero beyond M / K)
-__device__ __forceinline__ void load_a8(const float* __restrict__ A, int lda, int K, int64_t grow, int64_t M, int k0,
-                                        float (&x)[8]) {
-  if (grow < M && k0 + 8 <= K && (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
-    const float4* p = reinterpret_cast<const float4*>(A + grow * lda + k0);
-    const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
-    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = (grow < M && k0 + e < K) ? __ldg(A + grow * lda + k0 + e) : 0.f;
-  }
-}
-
-__global__ void __launch_bounds__(kXThreads, 1) tcx_gemm_kernel(XGemmArgs g) {
+__global__ void __launch_bounds__(kGThreads, 1) tcx_gemm_kernel(XGemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * 256;
-  const int N = g.N;
+  const int N = g.N, NU = tcx_nu(N), nblocks = N / NU;
   const int ks1 = (g.K1 + 15) / 16, ks2 = (g.K2 + 15) / 16, ksteps = ks1 + ks2;
+  const int64_t n_units = ((g.M + 255) / 256) * nblocks;      // unit = row block * nblocks + column block
+  const int64_t first = blockIdx.x, stride = gridDim.x;
   if (tid == 0) {
-    for (int i = 0; i < kGStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.a_ready[i], 8); mbar_init(&sm.empty[i], 1); }
-    mbar_init(&sm.acc_ready, 1);
+    // empty / acc_ready: one tcgen05.commit from EACH of the two issuing threads
+    for (int i = 0; i < kGStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.a_ready[i], 8); mbar_init(&sm.empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc_ready[i], 2); mbar_init(&sm.acc_free[i], 4); }
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<512>(&sm.tmem_base);
+  for (int i = tid; i < N; i += kGThreads) sm.bias[i] = g.bias != nullptr ? __ldg(g.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  const uint32_t stage_bytes = 96u * (uint32_t)N;
+  const uint32_t stage_bytes = 96u * (uint32_t)NU;
 
   if (warp == 9) {
-    // ---- weight-operand producer: one bulk copy per K = 16 step ----
+    // ---- weight-operand producer: one bulk copy per (unit, K = 16 step) ----
     if (lane == 0) {
-      for (int kt = 0; kt < ksteps; ++kt) {
-        const int s = kt % kGStages;
-        if (kt >= kGStages) mbar_wait(&sm.empty[s], ((kt / kGStages) - 1) & 1);
-        const uint8_t* src = (kt < ks1) ? g.B1 + (size_t)kt * stage_bytes : g.B2 + (size_t)(kt - ks1) * stage_bytes;
-        mbar_arrive_expect_tx(&sm.full[s], stage_bytes);
-        tma_load_1d(sm.b[s], src, stage_bytes, &sm.full[s]);
+      uint32_t it = 0;
+      for (int64_t u = first; u < n_units; u += stride) {
+        const int nb = (int)(u % nblocks);
+        for (int kt = 0; kt < ksteps; ++kt, ++it) {
+          const uint32_t s = it % kGStages;
+          if (it >= (uint32_t)kGStages) mbar_wait(&sm.empty[s], ((it / kGStages) - 1) & 1);
+          const uint8_t* src = (kt < ks1) ? g.B1 + ((size_t)nb * ks1 + kt) * stage_bytes
+                                          : g.B2 + ((size_t)nb * ks2 + (kt - ks1)) * stage_bytes;
+          mbar_arrive_expect_tx(&sm.full[s], stage_bytes);
+          tma_load_1d(sm.b[s], src, stage_bytes, &sm.full[s]);
+        }
       }
     }
-  } else if (warp == 8) {
-    // ---- MMA issuer: per step and tile six bf16 x bf16 products into the tile's fp32 accumulator ----
+  } else if (warp == 8 || warp == 14) {
+    // ---- MMA issuers: per step six bf16 x bf16 products into the fp32 accumulator of THIS thread's tile.  Two
+    //      threads because tcgen05.mma holds its issuer for ~160 cycles per N = 128 MMA whose pipe time is 64
+    //      (DESIGN.md §4 note 10): one thread alone ran the pipe at 40 %.  Each accumulator has ONE issuer, so the
+    //      fp32 summation order -- every output bit -- is fixed ----
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
-      for (int kt = 0; kt < ksteps; ++kt) {
-        const int s = kt % kGStages;
-        const uint32_t ph = (kt / kGStages) & 1;
-        mbar_wait(&sm.full[s], ph);
-        mbar_wait(&sm.a_ready[s], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
-#pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
+      const int tile = warp == 8 ? 0 : 1;
+      const uint32_t idesc = umma_idesc_bf16(128, NU, 0, 0);
+      uint32_t it = 0, un = 0;
+      for (int64_t u = first; u < n_units; u += stride, ++un) {
+        const uint32_t slot = 0;
+        if (un >= 1) {   // the epilogue warps have drained the previous unit (the accumulators fill the TMEM)
+          mbar_wait(&sm.acc_free[slot], (un - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kt = 0; kt < ksteps; ++kt, ++it) {
+          const uint32_t s = it % kGStages, ph = (it / kGStages) & 1;
+          mbar_wait(&sm.full[s], ph);
+          mbar_wait(&sm.a_ready[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
             const uint64_t da = umma_smem_desc(a0 + tile * 12288 + kProdA[p] * 4096, 2048, 128);
-            const uint64_t db = umma_smem_desc(b0 + kProdB[p] * 32 * N, 16 * N, 128);
+            const uint64_t db = umma_smem_desc(b0 + kProdB[p] * 32 * NU, 16 * NU, 128);
             umma_bf16(tmem + tile * 256, da, db, idesc, (kt > 0 || p > 0) ? 1u : 0u);
           }
+          umma_commit(&sm.empty[s]);
         }
-        umma_commit(&sm.empty[s]);
+        umma_commit(&sm.acc_ready[slot]);
       }
-      umma_commit(&sm.acc_ready);
     }
-  } else {
-    // ---- compute warps: thread = one row of one of the two tiles; it splits the row's 16 reduction columns of every
-    //      K = 16 step (the next step's are already in flight), then the epilogue ----
-    const int tile = tid >> 7, row = tid & 127;
-    const int64_t grow = m0 + tile * 128 + row;
-    auto fetch = [&](int kt, float (&lo)[8], float (&hi)[8]) {
+  } else if (warp < 8) {
+    // ---- A-split warps: warp w owns rows 32 w .. 32 w + 31 of the 256-row unit (tile w >> 2).  One load instruction
+    //      covers 8 rows x 64 contiguous bytes (lane = (row & 7) * 4 + quarter): 8 lines / 16 fully used sectors per
+    //      request.  (One row per lane -- 32 lines, half-used sectors per request -- ran the loop at the L1 tag rate:
+    //      ncu showed these warps waiting on their loads although three steps were in flight.)  The quarter's four
+    //      values become 8 bytes of each split operand: a warp's store is two contiguous 128-byte runs (conflict
+    //      free).  Three steps are kept in flight in a register ring (compile-time index in the 4x unrolled body). ----
+    const int tile = warp >> 2, r8 = lane >> 2, qk = lane & 3;
+    const int row0 = (warp & 3) * 32 + r8;                      // + 8 j, j = 0..3
+    int64_t n_mine = 0;
+    for (int64_t u = first; u < n_units; u += stride) ++n_mine;
+    const int64_t total = n_mine * ksteps;
+    auto fetch = [&](int64_t gi, float4 (&x)[4]) {
+      const int64_t un = gi / ksteps;
+      const int kt = (int)(gi - un * ksteps);
+      const int64_t rb = (first + un * stride) / nblocks;
+      const int64_t grow = rb * 256 + tile * 128 + row0;
       const bool second = kt >= ks1;
       const float* A = second ? g.A2 : g.A1;
-      const int lda = second ? g.lda2 : g.lda1, K = second ? g.K2 : g.K1, k0 = (second ? kt - ks1 : kt) * 16;
-      load_a8(A, lda, K, grow, g.M, k0, lo);
-      load_a8(A, lda, K, grow, g.M, k0 + 8, hi);
+      const int lda = second ? g.lda2 : g.lda1, K = second ? g.K2 : g.K1, k0 = (second ? kt - ks1 : kt) * 16 + qk * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = load_a4(A, lda, K, grow + 8 * j, g.M, k0);
     };
-    // The rows are 64 bytes per step and thread: with one step in flight the loop ran at the memory LATENCY (~4,000
-    // cycles per step against 1,536 of MMA time).  Three steps are kept in flight in a register ring (the ring index
-    // is a compile-time constant of the 4x unrolled body).
-    float xlo[4][8], xhi[4][8];
+    float4 xr[4][4];
 #pragma unroll
     for (int u = 0; u < 3; ++u)
-      if (u < ksteps) fetch(u, xlo[u], xhi[u]);
-    for (int kt0 = 0; kt0 < ksteps; kt0 += 4) {
+      if (u < total) fetch(u, xr[u]);
+    for (int64_t g0 = 0; g0 < total; g0 += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int kt = kt0 + u;
-        if (kt < ksteps) {
-          if (kt + 3 < ksteps) fetch(kt + 3, xlo[(u + 3) & 3], xhi[(u + 3) & 3]);
-          uint4 p1, p2, p3, q1, q2, q3;
-          split3x8(xlo[u], p1, p2, p3);
-          split3x8(xhi[u], q1, q2, q3);
-          const int s = kt % kGStages;
-          if (kt >= kGStages) mbar_wait(&sm.empty[s], ((kt / kGStages) - 1) & 1);
-          uint8_t* dst = sm.a[s] + tile * 12288 + row * 16;
-          *reinterpret_cast<uint4*>(dst) = p1;
-          *reinterpret_cast<uint4*>(dst + 2048) = q1;
-          *reinterpret_cast<uint4*>(dst + 4096) = p2;
-          *reinterpret_cast<uint4*>(dst + 4096 + 2048) = q2;
-          *reinterpret_cast<uint4*>(dst + 8192) = p3;
-          *reinterpret_cast<uint4*>(dst + 8192 + 2048) = q3;
+        const int64_t gi = g0 + u;
+        if (gi < total) {
+          if (gi + 3 < total) fetch(gi + 3, xr[(u + 3) & 3]);
+          uint2 p1[4], p2[4], p3[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split3x4(xr[u][j], p1[j], p2[j], p3[j]);
+          const uint32_t it = (uint32_t)gi, s = it % kGStages;
+          if (it >= (uint32_t)kGStages) mbar_wait(&sm.empty[s], ((it / kGStages) - 1) & 1);
+          // chunk (qk >> 1) of the step, row row0 + 8 j, half (qk & 1) of the 16-byte vector
+          uint8_t* dst = sm.a[s] + tile * 12288 + (qk >> 1) * 2048 + row0 * 16 + (qk & 1) * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint2*>(dst + j * 128) = p1[j];
+            *reinterpret_cast<uint2*>(dst + j * 128 + 4096) = p2[j];
+            *reinterpret_cast<uint2*>(dst + j * 128 + 8192) = p3[j];
+          }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.a_ready[s]);
         }
       }
     }
-    // ---- epilogue: TMEM lane quadrant = warp & 3 (rows), column half = warp >> 2, both tiles ----
-    mbar_wait(&sm.acc_ready, 0);
-    tc_fence_after();
-    const int q = warp & 3, hcol = warp >> 2;
+  } else {
+    // ---- epilogue warps 10..13: TMEM lane quadrant = warp & 3; both tiles, all NU columns of the unit ----
+    const int q = warp & 3;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int ncol_half = N / 2;                               // N is a multiple of 64
+    uint32_t un = 0;
+    for (int64_t u = first; u < n_units; u += stride, ++un) {
+      const uint32_t slot = 0;
+      const int64_t rb = u / nblocks;
+      const int cb = (int)(u % nblocks) * NU;
+      mbar_wait(&sm.acc_ready[slot], un & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int tl = 0; tl < 2; ++tl) {
-      const int64_t orow = m0 + tl * 128 + q * 32 + lane;
-      for (int c0 = hcol * ncol_half; c0 < (hcol + 1) * ncol_half; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + lane_base + tl * 256 + c0, v);        // warp-collective: outside the row guard
-        if (orow < g.M) {
+      for (int tl = 0; tl < 2; ++tl) {
+        const int64_t orow = rb * 256 + tl * 128 + q * 32 + lane;
+        const bool live = orow < g.M;
+        for (int c0 = 0; c0 < NU; c0 += 32) {
+          const int col = cb + c0;
+          uint32_t v[32];
+          tmem_ld32_issue(tmem + lane_base + tl * 256 + c0, v);   // warp-collective: outside the row guard
+          // the ReLU' mask row (dgrad) is fetched while the TMEM load is in flight
+          float4 mk[8];
+          if (g.epi == 3 && live) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if (g.bias != nullptr) {
-              // (scalar loads: the flat Keras-order parameter buffer is not 16-byte aligned past the 1-wide sigma bias)
-              o.x += __ldg(g.bias + c0 + i); o.y += __ldg(g.bias + c0 + i + 1);
-              o.z += __ldg(g.bias + c0 + i + 2); o.w += __ldg(g.bias + c0 + i + 3);
+            for (int i = 0; i < 8; ++i) mk[i] = __ldg(reinterpret_cast<const float4*>(g.mask + orow * g.ldmask + col) + i);
+          }
+          tmem_ld32_wait(v);
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sm.bias[col + 4 * i]);
+              float4 o = make_float4(__uint_as_float(v[4 * i]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y,
+                                     __uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w);
+              if (g.epi == 1) {          // EPI_RELU
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              } else if (g.epi == 3) {   // EPI_MASK: C = acc * (mask > 0)
+                o.x = mk[i].x > 0.f ? o.x : 0.f; o.y = mk[i].y > 0.f ? o.y : 0.f;
+                o.z = mk[i].z > 0.f ? o.z : 0.f; o.w = mk[i].w > 0.f ? o.w : 0.f;
+              }
+              *reinterpret_cast<float4*>(g.C + orow * g.ldc + col + 4 * i) = o;
             }
-            if (g.epi == 1) {          // EPI_RELU
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            } else if (g.epi == 3) {   // EPI_MASK: C = acc * (mask > 0)
-              const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + orow * g.ldmask + c0 + i));
-              o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-              o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-            }
-            *reinterpret_cast<float4*>(g.C + orow * g.ldc + c0 + i) = o;
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_free[slot]);
     }
   }
   tc_fence_before();
@@ -256,11 +319,10 @@ tcx_wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __res
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t mb = (int64_t)blockIdx.x * slab, me = min(mb + slab, M);
   const int nst = (int)((me - mb + kWSamples - 1) / kWSamples);
-  const int nch = N / 8;                             // 8-wide feature chunks of Z
   const int halves = (K + 127) / 128;                // 128-row accumulator blocks (TMEM columns h * 256)
   if (tid == 0) {
-    for (int i = 0; i < kWStages; ++i) { mbar_init(&sm.ready[i], 8); mbar_init(&sm.empty[i], 1); }
-    mbar_init(&sm.acc_ready, 1);
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&sm.ready[i], 8); mbar_init(&sm.empty[i], 2); }
+    mbar_init(&sm.acc_ready, 2);
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<512>(&sm.tmem_base);
@@ -269,15 +331,18 @@ tcx_wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __res
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    // two issuing threads, one per 128-row accumulator block h (a single thread runs the pipe at ~2/3: tcgen05.mma
+    // holds its issuer); with K <= 128 the second one only keeps the barrier counts
     if (lane == 0 && nst > 0) {
+      const int h = warp - 8;
       const uint32_t idesc = umma_idesc_bf16(128, N, 1, 1);
       for (int st = 0; st < nst; ++st) {
         const int s = st % kWStages;
         mbar_wait(&sm.ready[s], (st / kWStages) & 1);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sm.a[s]), z0 = smem_u32(sm.z[s]);
-        for (int h = 0; h < halves; ++h) {
+        if (h < halves) {
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
 #pragma unroll
@@ -287,42 +352,56 @@ tcx_wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __res
               umma_bf16(tmem + h * 256, da, dz, idesc, (st > 0 || p > 0 || ks > 0) ? 1u : 0u);
             }
           }
+          umma_commit(&sm.empty[s]);
+        } else {
+          mbar_arrive(&sm.empty[s]);
         }
-        umma_commit(&sm.empty[s]);
       }
-      umma_commit(&sm.acc_ready);
+      if (h < halves) umma_commit(&sm.acc_ready);
+      else mbar_arrive(&sm.acc_ready);
     }
   } else if (warp < 8) {
-    // ---- compute warps: lane = sample of the stage, the warp walks the feature chunks (conflict-free smem stores,
-    //      32-byte global sectors fully used) ----
+    // ---- compute warps: one load instruction covers 8 samples x 64 contiguous bytes (lane = (sample & 7) * 4 +
+    //      quarter; the quarter's 4 features are 8 bytes of each split operand), groups of 16 features are dealt
+    //      round-robin to the warps; all of a stage's loads are issued before the first is used ----
+    const int s8 = lane >> 2, qk = lane & 3;
+    const int ga = 8 * halves, gz = N / 16;            // 16-feature groups of A (zero-filled to 128 rows) and Z
     for (int st = 0; st < nst; ++st) {
       const int s = st % kWStages;
-      const int64_t r = mb + (int64_t)st * kWSamples + lane;
-      const bool live = r < me;
-#pragma unroll 1
-      for (int op = 0; op < 2; ++op) {
-        const float* src = op ? Z : A;
-        const int ld = op ? ldz : lda, width = op ? N : K;
-        uint8_t* dst = op ? sm.z[s] : sm.a[s];
-        const int cmax = op ? nch : 16 * halves;       // A: zero-fill up to the next 128-row block
-        // this warp's (up to four) feature chunks: all loads first, then split + store
-        float x[4][8];
+      const int64_t r0 = mb + (int64_t)st * kWSamples + s8;
+      float4 xa[2][4], xz[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cidx = warp + 8 * j;
-          if (cidx < cmax) load_a8(src, ld, width, live ? r : me, me, cidx * 8, x[j]);
+      for (int gi = 0; gi < 2; ++gi) {
+        const int ga_i = warp + 8 * gi;
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+          const int64_t r = r0 + 8 * sb;
+          if (ga_i < ga) xa[gi][sb] = load_a4(A, lda, K, r < me ? r : M, M, ga_i * 16 + qk * 4);
+          if (ga_i < gz) xz[gi][sb] = load_a4(Z, ldz, N, r < me ? r : M, M, ga_i * 16 + qk * 4);
         }
-        if (op == 0 && st >= kWStages) mbar_wait(&sm.empty[s], ((st / kWStages) - 1) & 1);
+      }
+      if (st >= kWStages) mbar_wait(&sm.empty[s], ((st / kWStages) - 1) & 1);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cidx = warp + 8 * j;
-          if (cidx < cmax) {
-            uint4 p1, p2, p3;
-            split3x8(x[j], p1, p2, p3);
-            uint8_t* d = dst + cidx * 512 + lane * 16;
-            *reinterpret_cast<uint4*>(d) = p1;
-            *reinterpret_cast<uint4*>(d + 16384) = p2;
-            *reinterpret_cast<uint4*>(d + 32768) = p3;
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g_i = warp + 8 * gi;
+        // chunk 2 g + (qk >> 1), sample s8 + 8 sb, half (qk & 1) of the 16-byte vector
+        const int off = (2 * g_i + (qk >> 1)) * 512 + s8 * 16 + (qk & 1) * 8;
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+          uint2 p1, p2, p3;
+          if (g_i < ga) {
+            split3x4(xa[gi][sb], p1, p2, p3);
+            uint8_t* d = sm.a[s] + off + sb * 128;
+            *reinterpret_cast<uint2*>(d) = p1;
+            *reinterpret_cast<uint2*>(d + 16384) = p2;
+            *reinterpret_cast<uint2*>(d + 32768) = p3;
+          }
+          if (g_i < gz) {
+            split3x4(xz[gi][sb], p1, p2, p3);
+            uint8_t* d = sm.z[s] + off + sb * 128;
+            *reinterpret_cast<uint2*>(d) = p1;
+            *reinterpret_cast<uint2*>(d + 16384) = p2;
+            *reinterpret_cast<uint2*>(d + 32768) = p3;
           }
         }
       }
@@ -383,7 +462,8 @@ int launch_gemm_tc(const GemmArgs& g, const void* blob1, const void* blob2, cuda
   if (x.A2 == nullptr) x.K2 = 0;
   const size_t smem = sizeof(GemmSmem);
   KN_CUDA(cudaFuncSetAttribute(tcx_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tcx_gemm_kernel<<<(unsigned)cdiv(g.M, 256), kXThreads, smem, st>>>(x);
+  const int64_t n_units = cdiv(g.M, 256) * (g.N / tcx_nu(g.N));
+  tcx_gemm_kernel<<<(unsigned)std::min<int64_t>(n_units, kNumSMs), kGThreads, smem, st>>>(x);
   KN_LAUNCH_CHECK();
   return KNERF_OK;
 }

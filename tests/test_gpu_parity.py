@@ -516,8 +516,8 @@ def test_model_train_two_steps_golden():
                 m = min(v.numel(), 32)
                 got, want = v.reshape(-1)[:m].cpu().numpy(), g[f"s{step}_param_{name}_head"][k][:m]
                 # Adam's first steps move every weight by ~lr * sign(g): where the gradient is ~0 the sign is noise,
-                # so 2 * lr is all that can be said there ...
-                np.testing.assert_allclose(got, want, atol=2.1e-3)
+                # so 2 * lr per step taken is all that can be said there ...
+                np.testing.assert_allclose(got, want, atol=2.1e-3 * (step + 1))
                 # ... but where the reference's gradient is clearly non-zero (coarse network, first step: the
                 # gradients themselves agree to 5e-5 * max) the update must be the reference's, to 1e-5
                 if name == "coarse" and step == 0:
