@@ -229,12 +229,14 @@ class NeRF:
             lib = _lib.load()
             nbytes = lib.knerf_packed_weight_bytes(C.byref(self.cfg))
             if nbytes <= 0:
-                # the tcgen05 chain kernels implement the 8x256 / skip 4 / L = 10,4 model of the reference's defaults;
-                # any other shape its CLI accepts (--num_units, --num_layers, --skip_layer, --pos_emb_*) runs in the
-                # fp32 SIMT mode -- loudly
-                logging.warning("precision='bf16' is not available for this model shape (%s); using the fp32 mode",
+                # the fused bf16 chain kernels implement the 8x256 / skip 4 / L = 10,4 model of the reference's
+                # defaults; any other shape its CLI accepts (--num_units, --num_layers, --skip_layer, --pos_emb_*)
+                # runs in the fp32_tc mode -- per-layer tcgen05 GEMMs for every layer whose width is a multiple of 64,
+                # SIMT FFMA for the others -- and says so
+                logging.warning("precision='bf16' is not available for this model shape (%s); using precision="
+                                "'fp32_tc' (fp32-grade per-layer tensor-core GEMMs)",
                                 lib.knerf_last_error().decode() or "unsupported configuration")
-                self.precision, self._prec = "fp32", _lib.FP32
+                self.precision, self._prec = "fp32_tc", _lib.FP32_TC
         self._prec_flags = self._prec | (_lib.TC_ORDERED if self.reproducible else 0)
         if self._prec == _lib.BF16:
             for name in ("coarse", "fine"):

@@ -137,3 +137,42 @@ def test_class_api_accepts_dlpack_producers():
     o1 = ut.render_image_depth_chunk(rgb, sig, t)
     o2 = ut.render_image_depth_chunk(Foreign(rgb), Foreign(sig), Foreign(t))
     assert all(torch.equal(x, y) for x, y in zip(o1, o2))
+
+
+def test_bf16_request_on_other_shape_falls_back_loudly(caplog):
+    """`--precision bf16` is the scripts' default, and the reference's CLI accepts any --num_units / --num_layers /
+    --skip_layer / --pos_emb_*: a shape the fused bf16 kernels do not implement must train (fp32_tc mode), not raise,
+    and must say so."""
+    import logging
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    mlp_mod.set_seed(1)
+    m = K.NeRF(precision="bf16", n_layers=4, dense_units=128, skip_layer=2, pos_emb_xyz=6, pos_emb_dir=2)
+    with caplog.at_level(logging.WARNING):
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=8, image_width=16, ray_chunks=64,
+                  white_background=True)
+    assert m.precision == "fp32_tc" and any("fp32_tc" in r.message for r in caplog.records)
+    rng = np.random.default_rng(0)
+    pose = K.pose_spherical(10.0, -30.0, 4.0)
+    o, d, t = K.RaysGenerator(K.get_focal_from_fov(0.69, 16), 16, 8, 2.0, 6.0, 64)(pose, seed=3)
+    images = rng.uniform(0, 1, (1, 8, 16, 4)).astype(np.float32)
+    logs = [m.train_step((images, (o[None], d[None], t[None])), seed=5 + i) for i in range(3)]
+    assert all(np.isfinite(l["fine_loss"]) for l in logs) and logs[2]["coarse_loss"] != logs[0]["coarse_loss"]
+
+
+def test_custom_loss_is_refused_and_initializers_accepted():
+    import keras_nerf_b200 as K
+    m = K.NeRF(precision="fp32")
+    with pytest.raises(NotImplementedError):
+        m.compile(optimizer="adam", loss=lambda a, b: abs(a - b), batch_size=1, image_height=4, image_width=4,
+                  ray_chunks=16)
+
+    def compute_distributed_loss(y_true, y_pred):      # train.py:130-136 wraps MeanSquaredError under this name
+        return ((y_true - y_pred) ** 2).mean()
+    m.compile(optimizer="adam", loss=compute_distributed_loss, batch_size=1, image_height=4, image_width=4, ray_chunks=16)
+    for init in ("he_normal", "glorot_normal", "lecun_uniform", "zeros"):
+        net = K.NeRFMLP(n_layers=2, dense_units=16, skip_layer=4, initializer=init).build(15, 9)
+        w = net.trainable_variables[0]
+        assert bool(torch.isfinite(w).all()) and (init != "zeros" or float(w.abs().max()) == 0.0)
+    with pytest.raises(NotImplementedError):
+        K.NeRFMLP(initializer="orthogonal_typo")
