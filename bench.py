@@ -144,7 +144,7 @@ def cpu_train_rays_per_sec(n_rays=CPU_SAMPLE_RAYS, steps=1, warmup=0, render=Fal
     return res, dt
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -160,7 +160,7 @@ def run_reference(args):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "render": {"metric": "render_s_per_frame_128x128", "value": cb.get("render_128x128_s"), "unit": "s"},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(precision, ray_chunks):
@@ -184,8 +184,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary 800x800 render metric")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner at communicator
+    # creation) are sent to stderr until the line is written
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -307,7 +317,7 @@ def main():
         line["cpu_baseline"], _ = cpu_train_rays_per_sec()      # rank 0's host cores; the other ranks wait
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     if strategy is not None:
         strategy.barrier()
         torch.distributed.destroy_process_group()
