@@ -267,15 +267,35 @@ def main():
     model._losses.zero_()
 
     # ---- e2e: public API, pinned host inputs, H2D + train_step + metrics D2H inside the timed region ----
-    for i in range(2):
+    # input pipeline of a user's training loop (what tf.data's prefetch does for the reference, loader.py:106): the
+    # host -> device copy of step i + 1 is issued on a copy stream while step i computes.  Every step's copy is inside
+    # the timed region; the first one is not hidden.
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload(i):
         img, rays = host[i % nb]
-        model.train_step((img.to(dev, non_blocking=True), tuple(r.to(dev, non_blocking=True) for r in rays)))
+        with torch.cuda.stream(copy_stream):
+            out = (img.to(dev, non_blocking=True), tuple(r.to(dev, non_blocking=True) for r in rays))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return out, ev
+
+    def e2e_loop(n):
+        logs, nxt = {}, upload(0)
+        for i in range(n):
+            (img, rays), ev = nxt
+            torch.cuda.current_stream().wait_event(ev)
+            if i + 1 < n:
+                nxt = upload(i + 1)
+            logs = model.train_step((img, rays))
+            for x in (img,) + tuple(rays):
+                x.record_stream(torch.cuda.current_stream())
+        return logs
+
+    e2e_loop(2)
     sync()
     t0 = time.perf_counter()
-    logs = {}
-    for i in range(args.steps):
-        img, rays = host[i % nb]
-        logs = model.train_step((img.to(dev, non_blocking=True), tuple(r.to(dev, non_blocking=True) for r in rays)))
+    logs = e2e_loop(args.steps)
     sync()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
@@ -307,7 +327,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(precision, ray_chunks),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 8 + 4 * 4, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": 8 + 4 * 4, "ms_per_step": e2e_ms / args.steps,
+                    "pipeline": "step i + 1's H2D copy on a copy stream while step i computes; one D2H read per step"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
             "step_tflops": FLOP_TRAIN_PER_SAMPLE * (N_COARSE + N_COARSE + N_FINE) * RAYS_PER_GPU * world
             * args.steps / (ms * 1e-3) / 1e12,

@@ -378,9 +378,15 @@ class NeRF:
 
     # ---- metrics (nerf.py:306-330) ------------------------------------------------------------
     def update_and_return_metrics(self, images, coarse_images, fine_images, coarse_loss, fine_loss):
+        """coarse_loss / fine_loss: floats, or ONE device tensor [2] (then `fine_loss` is None) that is read back
+        together with the PSNR / SSIM values in a single device -> host copy"""
         mc = image_metrics(images, coarse_images)
         mf = image_metrics(images, fine_images)
-        vals = torch.stack([mc, mf]).cpu()                                        # one device -> host read
+        if torch.is_tensor(coarse_loss) and fine_loss is None:
+            flat = torch.cat([torch.stack([mc, mf]).reshape(-1), coarse_loss.reshape(-1)]).cpu()   # the step's only sync
+            vals, (coarse_loss, fine_loss) = flat[:-2].reshape(2, 2, -1), flat[-2:].tolist()
+        else:
+            vals = torch.stack([mc, mf]).cpu()                                    # one device -> host read
         self.coarse_loss_tracker.update_state(float(coarse_loss))
         self.coarse_psnr_metric.update_state(vals[0, 0])
         self.corase_ssim_metric.update_state(vals[0, 1])
@@ -457,8 +463,7 @@ class NeRF:
                 logging.warning('Fine Gradient is zero')
         self.apply_gradients()
         imgs = _lib.dev(images, self.device)[..., :3]
-        lc, lf = losses.tolist()
-        return self.update_and_return_metrics(imgs, ci, fi, lc, lf)
+        return self.update_and_return_metrics(imgs, ci, fi, losses, None)   # losses + metrics: one host read
 
     def test_step(self, inputs, u_fine=None, seed=None):
         # nerf.py:475-497
