@@ -134,6 +134,18 @@ def dev(x, device, dtype=torch.float32) -> torch.Tensor:
     return torch.as_tensor(x, dtype=dtype, device=device).contiguous()
 
 
+def seed_stream(tag: int, advance: int = 0):
+    """Philox seed stream of this process for draws the caller did not pin (`seed=None`): an `itertools.count` keyed
+    by `tag` (which generator), the torch seed (torch.manual_seed; the scripts' tf.random.set_seed) and the RANK, so
+    the replicas of a data-parallel run draw independent samples (every replica of a MirroredStrategy has its own
+    tf.random stream too); `advance` skips ahead (a resumed run must not replay epoch 0's draws)."""
+    import itertools
+    rank = int(os.environ.get("RANK", "0"))
+    base = (tag + (torch.initial_seed() & 0xFFFFFFFF) * 0x9E3779B1 + rank * 0x9E3779B97F4A7C15
+            + advance * 0x632BE59BD9B4E019)
+    return itertools.count(base & 0x3FFFFFFFFFFFFFFF)
+
+
 def default_device() -> torch.device:
     if not torch.cuda.is_available():
         raise KnerfError("keras_nerf_b200 needs a CUDA device (no CPU fallback)")

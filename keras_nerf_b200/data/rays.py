@@ -8,7 +8,7 @@ import torch
 
 from .. import _lib
 
-_seed_counter = itertools.count(0x5EED0000)
+_seed_counter = _lib.seed_stream(0x5EED0000)
 
 
 class RaysGenerator:

@@ -102,15 +102,7 @@ def image_metrics(a: torch.Tensor, b: torch.Tensor, max_val: float = 1.0):
     return out
 
 
-def _seed_base():
-    """Philox seed stream of this process for draws the caller did not pin (`seed=None`): keyed by the torch seed
-    (torch.manual_seed / tf.random.set_seed in the scripts) and by the RANK, so the replicas of a data-parallel run
-    draw independent fine samples (every replica of a MirroredStrategy gets its own tf.random stream too)."""
-    rank = int(os.environ.get("RANK", "0"))
-    return (0xC0A45E00 + (torch.initial_seed() & 0xFFFFFFFF) * 0x9E3779B1 + rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
-
-
-_seed_counter = itertools.count(_seed_base())
+_seed_counter = _lib.seed_stream(0xC0A45E00)      # fine-sample draws of calls that pass neither `u_fine` nor `seed`
 
 
 class NeRF:
@@ -486,6 +478,9 @@ class NeRF:
 
     # ---- a thin Keras-style fit loop (train.py:151-157, train_single.py:137-143) ---------------
     def fit(self, dataset, epochs=1, validation_data=None, callbacks=None, initial_epoch=0, verbose=1):
+        global _seed_counter
+        if initial_epoch:       # a resumed run continues the draw sequence instead of replaying epoch 0's
+            _seed_counter = _lib.seed_stream(0xC0A45E00, advance=int(initial_epoch))
         callbacks = list(callbacks or [])
         for cb in callbacks:
             if hasattr(cb, "set_model"):

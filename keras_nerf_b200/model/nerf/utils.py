@@ -8,7 +8,7 @@ import torch
 
 from ... import _lib
 
-_seed_counter = itertools.count(0xF17E0000)
+_seed_counter = _lib.seed_stream(0xF17E0000)
 
 
 class NeRFUtils:
