@@ -12,10 +12,6 @@ namespace knerf {
 
 constexpr int kWarpsPerBlock = 8;
 
-struct RaySamples {
-  // per-lane registers for NB blocks of 32 samples
-};
-
 template <int NB, bool PACKED>
 __device__ __forceinline__ void load_ray(const float* __restrict__ rgbsigma, const float* __restrict__ rgb,
                                          const float* __restrict__ sigma, const float* __restrict__ t,

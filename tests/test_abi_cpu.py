@@ -81,6 +81,26 @@ def test_workspace_sizing_and_errors(lib):
         lib.call("knerf_adam_step", None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-7, 1, 1, None)
 
 
+def test_comm_entry_points_validate_arguments(lib):
+    """a14 behind the C ABI (knerf_comm_*, knerf_allreduce_grads, knerf_train_chunk_dp): argument validation happens
+    before NCCL or CUDA is touched, so it is checkable here; the collective itself is tests/test_gpu_multi.py"""
+    L = lib.load()
+    comm = C.c_void_p()
+    assert L.knerf_comm_unique_id(None) == -1
+    assert L.knerf_comm_create(None, 0, 2, C.byref(comm)) == -1
+    ident = (C.c_ubyte * lib.COMM_ID_BYTES)()
+    assert L.knerf_comm_create(ident, 2, 2, C.byref(comm)) == -1 and b"rank 2 of 2" in L.knerf_last_error()
+    assert L.knerf_comm_adopt(None, 0, 1, C.byref(comm)) == -1
+    assert L.knerf_allreduce_grads(None, None, 10, None) == -1
+    assert L.knerf_comm_rank(None, None, None) == -1
+    assert L.knerf_comm_destroy(None) == 0                      # destroying nothing is fine
+    # the option bits live in the precision argument and do not disturb the sizing entry point
+    cfg = lib.Config(64, 128, 10, 4, 8, 256, 4, 0, 0)
+    base = L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32, 1)
+    assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32 | lib.TC_ORDERED | lib.BWD_DGRAD_ONLY, 1) == base
+    assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32_TC, 1) > base       # + the split weight operand blobs
+
+
 def test_product_path_has_no_cpu_fallback(lib):
     import torch
     from keras_nerf_b200 import NeRFUtils
