@@ -250,8 +250,10 @@ wgrad_kernel(const float* __restrict__ A, int lda, int K, const float* __restric
   }
 }
 
+// db != nullptr: the caller also wants db[N] += column sums of Z (the layer's bias gradient); *db_done tells whether
+// this launch took them along (the tensor-core kernel has every Z value in registers anyway) or a colsum launch is due
 static int launch_wgrad(const float* A, int lda, int K, const float* Z, int ldz, int N, int64_t M, float* dW,
-                        int ldw, cudaStream_t st, bool tc = false) {
+                        int ldw, cudaStream_t st, bool tc = false, float* db = nullptr, bool* db_done = nullptr) {
   if (M == 0 || K == 0 || N == 0) return KNERF_OK;
   if (N <= 4) {
     const int kb = (int)cdiv(K, 256);
@@ -262,7 +264,11 @@ static int launch_wgrad(const float* A, int lda, int K, const float* Z, int ldz,
     KN_LAUNCH_CHECK();
     return KNERF_OK;
   }
-  if (tc && tcx_wgrad_eligible(K, N)) return launch_wgrad_tc(A, lda, K, Z, ldz, N, M, dW, ldw, st);
+  if (tc && tcx_wgrad_eligible(K, N)) {
+    const bool fuse = db != nullptr && db_done != nullptr && !*db_done;
+    if (fuse) *db_done = true;
+    return launch_wgrad_tc(A, lda, K, Z, ldz, N, M, dW, ldw, fuse ? db : nullptr, st);
+  }
   const int tiles = (int)(cdiv(K, WBK) * cdiv(N, WBN));
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(M, 4 * WBM), cdiv((int64_t)kNumSMs * 8, tiles)));
   int64_t slab = align_up(cdiv(M, splits), WBM);
@@ -448,9 +454,13 @@ int fp32_backward_core(const Model& m, const float* params, const float* X0, int
     KN_TRY(launch_gemm(g, true, st));
   }
   // rgb_features (linear): dWg[:U] += F^T dG ; dWg[U:] += DIR^T dG ; dbg ; dF = dG @ Wg[:U]^T
-  KN_TRY(launch_wgrad(F, U, Lg.k_h, DG, U2, U2, rows, grads + Lg.w_off, U2, st, p.tc));
-  KN_TRY(launch_wgrad(DIR, ldd, Lg.k_x, DG, U2, U2, rows, grads + Lg.w_off + (int64_t)Lg.k_h * U2, U2, st, p.tc));
-  KN_TRY(launch_colsum(DG, U2, U2, rows, grads + Lg.b_off, st));
+  {
+    bool done = false;
+    KN_TRY(launch_wgrad(F, U, Lg.k_h, DG, U2, U2, rows, grads + Lg.w_off, U2, st, p.tc, grads + Lg.b_off, &done));
+    KN_TRY(launch_wgrad(DIR, ldd, Lg.k_x, DG, U2, U2, rows, grads + Lg.w_off + (int64_t)Lg.k_h * U2, U2, st, p.tc,
+                        grads + Lg.b_off, &done));
+    if (!done) KN_TRY(launch_colsum(DG, U2, U2, rows, grads + Lg.b_off, st));
+  }
   {
     GemmArgs g{};
     g.A1 = DG; g.lda1 = U2; g.K1 = U2; g.B1 = params + Lg.w_off; g.ldb1 = U2; g.K2 = 0;
@@ -458,9 +468,13 @@ int fp32_backward_core(const Model& m, const float* params, const float* X0, int
     KN_TRY(launch_gemm(g, true, st, bwd_blob(m, p, ws, n + 2), nullptr));
   }
   // features (linear) + sigma head share the input h_last (and x after a trailing skip)
-  KN_TRY(launch_wgrad(Hl, U, Lf.k_h, D0, U, U, rows, grads + Lf.w_off, U, st, p.tc));
-  KN_TRY(launch_wgrad(X0, ldx, Lf.k_x, D0, U, U, rows, grads + Lf.w_off + (int64_t)Lf.k_h * U, U, st, p.tc));
-  KN_TRY(launch_colsum(D0, U, U, rows, grads + Lf.b_off, st));
+  {
+    bool done = false;
+    KN_TRY(launch_wgrad(Hl, U, Lf.k_h, D0, U, U, rows, grads + Lf.w_off, U, st, p.tc, grads + Lf.b_off, &done));
+    KN_TRY(launch_wgrad(X0, ldx, Lf.k_x, D0, U, U, rows, grads + Lf.w_off + (int64_t)Lf.k_h * U, U, st, p.tc,
+                        grads + Lf.b_off, &done));
+    if (!done) KN_TRY(launch_colsum(D0, U, U, rows, grads + Lf.b_off, st));
+  }
   KN_TRY(launch_wgrad(Hl, U, Ls.k_h, d_pre + 3, 4, 1, rows, grads + Ls.w_off, 1, st, p.tc));
   KN_TRY(launch_wgrad(X0, ldx, Ls.k_x, d_pre + 3, 4, 1, rows, grads + Ls.w_off + Ls.k_h, 1, st, p.tc));
   KN_TRY(launch_colsum(d_pre + 3, 4, 1, rows, grads + Ls.b_off, st));
@@ -475,9 +489,12 @@ int fp32_backward_core(const Model& m, const float* params, const float* X0, int
   float* other = D0;
   for (int i = n - 1; i >= 0; --i) {
     const LayerDesc& L = m.L[i];
-    if (i > 0) KN_TRY(launch_wgrad(H(i - 1), U, L.k_h, dz, U, U, rows, grads + L.w_off, U, st, p.tc));
-    KN_TRY(launch_wgrad(X0, ldx, L.k_x, dz, U, U, rows, grads + L.w_off + (int64_t)L.k_h * U, U, st, p.tc));
-    KN_TRY(launch_colsum(dz, U, U, rows, grads + L.b_off, st));
+    bool done = false;
+    if (i > 0)
+      KN_TRY(launch_wgrad(H(i - 1), U, L.k_h, dz, U, U, rows, grads + L.w_off, U, st, p.tc, grads + L.b_off, &done));
+    KN_TRY(launch_wgrad(X0, ldx, L.k_x, dz, U, U, rows, grads + L.w_off + (int64_t)L.k_h * U, U, st, p.tc,
+                        grads + L.b_off, &done));
+    if (!done) KN_TRY(launch_colsum(dz, U, U, rows, grads + L.b_off, st));
     if (i > 0) {  // dZ_{i-1} = (dZ_i @ W_i[:U]^T) * (h_{i-1} > 0)   (no gradient into the x / dir inputs)
       GemmArgs g{};
       g.A1 = dz; g.lda1 = U; g.K1 = U; g.B1 = params + L.w_off; g.ldb1 = U; g.K2 = 0;

@@ -20,8 +20,9 @@ int tcx_pack(const float* src, int ld, int N, int K, bool trans, void* blob, cud
 bool tcx_gemm_eligible(const GemmArgs& g);
 int launch_gemm_tc(const GemmArgs& g, const void* blob1, const void* blob2, cudaStream_t st);
 bool tcx_wgrad_eligible(int K, int N);
+// db != nullptr: also db[N] += column sums of Z
 int launch_wgrad_tc(const float* A, int lda, int K, const float* Z, int ldz, int N, int64_t M, float* dW, int ldw,
-                    cudaStream_t st);
+                    float* db, cudaStream_t st);
 
 struct Fp32Plan {
   int64_t rows;
