@@ -312,9 +312,20 @@ def main():
             render = render_ms_per_frame(precision, dev, strategy)
         except Exception as e:  # the secondary metric must never take the headline down
             render = {"error": str(e)[:200]}
+    def rank0_done(signal):
+        """rank 0 times the CPU baseline on the host cores: the other ranks must not spin meanwhile (an NCCL barrier
+        keeps one host thread per rank busy in cudaStreamSynchronize and slowed the 16-thread CPU leg 6x) -- they block
+        on the rendezvous store until rank 0 is through"""
+        store = torch.distributed.distributed_c10d._get_default_store()
+        if signal:
+            store.set("knerf_bench_rank0_done", "1")
+        else:
+            store.wait(["knerf_bench_rank0_done"])
+
     if rank != 0:
         if strategy is not None:
-            strategy.barrier()      # rank 0 is timing the CPU baseline
+            rank0_done(False)
+            strategy.barrier()
             torch.distributed.destroy_process_group()
         return
     peaks = load_peaks()
@@ -340,6 +351,7 @@ def main():
         line["cpu_baseline"] = None
     emit(line)
     if strategy is not None:
+        rank0_done(True)
         strategy.barrier()
         torch.distributed.destroy_process_group()
 
