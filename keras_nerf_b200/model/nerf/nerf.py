@@ -403,6 +403,11 @@ class NeRF:
         rc, nch = self.ray_chunks, self.sequential_chunks
         oob = self._sampler_flags()
         # data parallel: the all-reduce rides inside the LAST chunk's call (coarse half behind the coarse backward)
+        if getattr(self, "_grads_reduced", False):
+            # the accumulators already hold a cross-replica SUM: adding local gradients to it and reducing again
+            # would count the other replicas' share twice
+            raise RuntimeError("the accumulated gradients have been all-reduced: call apply_gradients() before the next "
+                               "accumulate_gradients(), or pass reduce=False to accumulate several batches first")
         comm, comm_stream = (None, None) if self.strategy is None or not reduce else self.strategy.knerf_comm()
         self._grads_reduced = comm is not None
         with torch.cuda.device(self.device):
