@@ -426,17 +426,11 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
               const float* wv = reinterpret_cast<const float*>(wq);
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
-                const int col = col0 + c8 * 8;
                 const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int j = (c8 * 8 + e) * 3;
                   pr += x[e] * wv[j]; pg += x[e] * wv[j + 1]; pb += x[e] * wv[j + 2];
-                }
-                if (save) {
-                  const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                                              pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-                  *reinterpret_cast<uint4*>(rec_t + kRecG + (col >> 3) * kChunkA + r * 16) = pk;
                 }
               }
             }

@@ -245,6 +245,8 @@ struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, fr
 struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; int8_t last_grp[2][kWMaxUnits]; };
 // mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
 //      3: X = h7^T dG into the fp32 scratch (tc_finish_kernel turns it into dW_features and dW_rgb_features[:256])
+//      4: Yd = PE(dir)^T d(rgb_pre) into the scratch (columns 0..2 of the d_pre operand; rgb kernel, tc_finish_kernel)
+// (mode 1 groups also leave Y = h7^T d(rgb_pre), columns 0..2 of the same accumulator, in the scratch)
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
@@ -287,20 +289,19 @@ static WTaskTable build_task_table() {
      // Units in order of first use; groups ordered so that each unit is released as early as possible.
     WTask& t = T.t[n++];
     const int h7 = kRecH0 + 7 * kHSBytes;
-    t.n_units = 5;
+    t.n_units = 4;
     t.u[0] = {0, h7, kWUnitBytes, -1, 0, 0, 0};                 // h7 features 0..127
     t.u[1] = {1, kDzG, kWUnitBytes, 10, 0, 0, 0};               // dG (its column sums = db_rgb_features)
     t.u[2] = {0, kRecDS, 8192, -1, 0, kDzP, 4096};              // PE(dir) (32 columns, 27 valid accumulator rows) and,
                                                                 // at +8192, the packed (d rgb_pre, d sigma_pre) operand
     t.u[3] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0, 0, 0};   // h7 features 128..255
-    t.u[4] = {0, kRecG, kWUnitBytes, -1, 0, 0, 0};              // rgb_features activations
     t.n_groups = 6;
     t.g[0] = {0, 1, 0, 128, -1, 0, 128, 0, 3, 0, 0, 0, 0};
-    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0, 0, 8192};
+    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0, 0, 8192};   // sigma kernel (column 3) + Y rows 0..127 (columns 0..2)
     t.g[2] = {3, 1, 128, 128, -1, 128, 128, 0, 3, 0, 0, 0, 0};
     t.g[3] = {3, 2, 400, 16, 8, 128, 128, 0, 1, 1, 0, 0, 8192};
     t.g[4] = {2, 1, 256, 128, 10, 256, 27, 0, 0, 0, 1, 0, 0};
-    t.g[5] = {4, 2, 416, 16, 11, 0, 128, 0, 2, 1, 1, 0, 8192};
+    t.g[5] = {2, 2, 416, 16, -1, 0, 27, 0, 4, 1, 1, 0, 8192};   // Yd = PE(dir)^T d(rgb_pre): A and B share the unit
     t.cost = 170;
     // the three N = 128 groups are the heavy ones: two on issuer 0, the third with the three N = 16 groups on issuer 1
     t.g[0].issuer = 0; t.g[2].issuer = 0; t.g[1].issuer = 1; t.g[3].issuer = 1; t.g[4].issuer = 1; t.g[5].issuer = 1;
@@ -427,7 +428,7 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               umma_bf16(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
             }
             if (t.last_grp[me][g.a] == gi) umma_commit(&sm.empty[sa]);
-            if (t.last_grp[me][g.b] == gi) umma_commit(&sm.empty[sb]);
+            if (g.b != g.a && t.last_grp[me][g.b] == gi) umma_commit(&sm.empty[sb]);
           }
           // units this issuer never reads: release them too (after their load has landed, so that the arrival
           // counts for this use of the slot and not for the previous one)
@@ -459,6 +460,7 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int e = 0; e < 8; ++e) bacc[u][e] = 0.f;
+      float pacc[3] = {0.f, 0.f, 0.f};          // this thread's row of the packed d_pre operand, summed over the tiles
       for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile) {
         int nb = 0;
         for (int k = 0; k < t.n_units; ++k, ++uit) {
@@ -474,6 +476,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               a[4] += bf16_lo(v.z); a[5] += bf16_hi(v.z); a[6] += bf16_lo(v.w); a[7] += bf16_hi(v.w);
             }
             ++nb;
+          }
+          if (t.u[k].bytes2 != 0) {   // the d_pre operand at +8192: [2 chunks][128 rows][8], chunk 0 = (r, g, b, sigma, 0..)
+            const uint2 v = *reinterpret_cast<const uint2*>(sm.slot[slot] + 8192 + ftid * 16);   // one row per thread: this
+            pacc[0] += bf16_lo(v.x); pacc[1] += bf16_hi(v.x); pacc[2] += bf16_lo(v.y);           // sits on the slot-release path
           }
           named_bar_sync(2, 128);               // all 128 readers are done with the slot
           if (ftid == 0) mbar_arrive(&sm.empty[slot]);
@@ -502,6 +508,13 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
           ++nb;
         }
       }
+      if (w.task == kNumTasks - 1) {   // heads task: sum d(rgb_pre) of this call for tc_finish_kernel
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const float sres = warp_sum(pacc[e]);
+          if (lane == 0) atomicAdd(xbuf + kXOffS + e, sres);
+        }
+      }
       mbar_wait(&sm.acc_done, done_par);
       done_par ^= 1;
       tc_fence_after();
@@ -523,8 +536,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
             } else if (g.mode == 1) {
               atomicAdd(grads + P.w_off[8] + g.row_base + row, v[3]);
+              float* dst = xbuf + kXOffY + (g.row_base + row) * 4;
+              atomicAdd(dst, v[0]); atomicAdd(dst + 1, v[1]); atomicAdd(dst + 2, v[2]);
             } else {
-              float* dst = grads + P.w_off[11] + row * 3;
+              float* dst = xbuf + kXOffYd + row * 4;
               atomicAdd(dst, v[0]); atomicAdd(dst + 1, v[1]); atomicAdd(dst + 2, v[2]);
             }
           }
@@ -546,8 +561,12 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 //   dW_g[j][n]      += sum_i W_f[i][j] X[i][n] + b_f[j] s[n]           (j < 256, n < 128; s = sum(dG) of this call)
 //   db_f[j]         += sum_n s[n] W_g[j][n]
 // One thread per output element; 12.6 M MAC per call, operands (384 KB) stay in L2.
+//   dW_c[k][c]      += sum_j W'[j][k] Y[j][c] + sum_i W_g[256+i][k] Yd[i][c] + b'[k] s3[c]     (k < 128, c < 3: the rgb kernel;
+//                      G^T d(rgb_pre) with G = h7 W' + PE(dir) W_g[256:] + b', Y = h7^T d(rgb_pre), Yd = PE(dir)^T d(rgb_pre),
+//                      s3 = sum d(rgb_pre); `fold` = the fp32 W' [256,128] and b' [128] of the packed weights)
 __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict__ params, TcParams P,
-                                                        const float* __restrict__ xbuf, float* __restrict__ grads) {
+                                                        const float* __restrict__ xbuf, float* __restrict__ grads,
+                                                        const float* __restrict__ fold) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const float* Wf = params + P.w_off[9];
   const float* Wg = params + P.w_off[10];
@@ -572,6 +591,14 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
     float acc = 0.f;
     for (int n = 0; n < 128; ++n) acc = fmaf(s[n], w[n], acc);
     grads[P.b_off[9] + j] += acc;
+  } else if (idx < 256 * 256 + 256 * 128 + 256 + 128 * 3) {
+    const int e = idx - (256 * 256 + 256 * 128 + 256), k = e / 3, c = e - k * 3;
+    const float* Y = xbuf + kXOffY;
+    const float* Yd = xbuf + kXOffYd;
+    float acc = fold[256 * 128 + k] * xbuf[kXOffS + c];
+    for (int j = 0; j < 256; ++j) acc = fmaf(fold[j * 128 + k], Y[j * 4 + c], acc);
+    for (int i = 0; i < 27; ++i) acc = fmaf(Wg[(256 + i) * 128 + k], Yd[i * 4 + c], acc);
+    grads[P.w_off[11] + e] += acc;
   }
 }
 
@@ -614,6 +641,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   if (parts & 2) {
     static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
     // items ~ 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 170 -> 217 + 36 + 41 = 294 items for 31 slabs
+    // (re-measured after the G record went away: heads cost 120 / 140 / 150 / 200 and 32 slabs x cost 136 are all slower)
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
     const int grid = std::min(n_items, kNumSMs);
@@ -622,7 +650,8 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
     KN_LAUNCH_CHECK();
-    tc_finish_kernel<<<(256 * 256 + 256 * 128 + 256 + 255) / 256, 256, 0, st>>>(params, P, xbuf, grads);
+    tc_finish_kernel<<<(256 * 256 + 256 * 128 + 256 + 128 * 3 + 255) / 256, 256, 0, st>>>(
+        params, P, xbuf, grads, reinterpret_cast<const float*>((const uint8_t*)packed + kFoldOff));
     KN_LAUNCH_CHECK();
   }
   return KNERF_OK;

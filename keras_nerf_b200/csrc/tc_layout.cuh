@@ -116,18 +116,24 @@ struct TcParams {
 constexpr int kRecXS = 0;                          // PE(xyz)      [8 chunks][128][8]   16 KB
 constexpr int kRecDS = 16384;                      // PE(dir)      [4 chunks][128][8]    8 KB (the next 8 KB are unused)
 constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
-constexpr int kRecG = kRecH0 + 8 * kHSBytes;       // rgb_features [16 chunks][128][8]  32 KB
-constexpr int kRecMask = kRecG + 32768;            // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
+// (the rgb_features activations G are NOT saved: G = h7 W' + PE(dir) W_g[256:] + b' is linear in records that are saved
+//  anyway, so the rgb kernel's gradient G^T d(rgb_pre) = W'^T (h7^T d(rgb_pre)) + W_g[256:]^T (PE(dir)^T d(rgb_pre))
+//  + b' (x) sum d(rgb_pre) comes from three columns the weight-gradient kernel computes anyway -- tc_finish_kernel)
+constexpr int kRecMask = kRecH0 + 8 * kHSBytes;    // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
 constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns h*128 + g*32 + (0..31) of row r;
                                                    //   bit i = column 2i, bit 16+i = column 2i+1 (bf16x2 packing order)
-constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 608 KB per 128 samples
+constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 576 KB per 128 samples
 // pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
 constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB
 constexpr int kDzG = 8 * kHSBytes;                 // d rgb_features 32 KB
 constexpr int kDzP = kDzG + 32768;                 // (d rgb_pre[3], d sigma_pre, 0...) [2 chunks][128][8]  4 KB
 constexpr int kDzBytes = kDzP + 4096;              // 548 KB per 128 samples
-// fp32 scratch at the head of the training workspace: X = h7^T dG [256 x 128], then sum(dG) [128]
-constexpr int kXFloats = 256 * 128 + 128;
+// fp32 scratch at the head of the training workspace: X = h7^T dG [256 x 128], sum(dG) [128], then for the rgb
+// kernel's gradient Y = h7^T d(rgb_pre) [256 x 4], Yd = PE(dir)^T d(rgb_pre) [32 x 4] and sum d(rgb_pre) [4]
+constexpr int kXOffY = 256 * 128 + 128;
+constexpr int kXOffYd = kXOffY + 256 * 4;
+constexpr int kXOffS = kXOffYd + 32 * 4;
+constexpr int kXFloats = kXOffS + 4;
 constexpr int kXBytes = ((kXFloats * 4 + 255) / 256) * 256;
 
 struct ChainSmem {
