@@ -19,10 +19,10 @@ FLOP_FWD_INFER_EXECUTED = 2 * (593_408 - 256 * 256 + 288 * 16)
 FLOP_TRAIN_PER_SAMPLE = 3_489_024          # fwd + dgrad + wgrad
 FLOP_WGRAD_PER_SAMPLE = 1_186_816          # every weight once more
 FLOP_DGRAD_PER_SAMPLE = FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE - FLOP_WGRAD_PER_SAMPLE
-# bf16 mode, algorithmic HBM bytes per sample (records of 576 KB + 548 KB per 128 samples)
+# bf16 mode, algorithmic HBM bytes per sample (records of 576 KB + 516 KB per 128 samples)
 BYTES_FWD_SAVE = 568 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
-BYTES_DGRAD = 8 * 32 + 548 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes the dZ record
-BYTES_WGRAD = 1164 * 1024 / 128                         # operand units of the 10 weight-gradient tasks
+BYTES_DGRAD = 8 * 32 + 516 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes dZ0..dZ7 + the d_pre operand
+BYTES_WGRAD = 1132 * 1024 / 128                         # operand units of the 10 weight-gradient tasks
 # measured DRAM traffic per sample (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture,
 # divided by the samples of that launch): profiles/ncu_traffic.json, written from the capture named inside it
 def _ncu_traffic():

@@ -10,8 +10,8 @@
 //     blobs are consumed as MN-major UMMA operands (same bytes, other axis; see tc_ptx.cuh), fp32 partial
 //     sums stay in TMEM across all tiles of a work item and are flushed once with red.global.add.f32; idle warps
 //     take the bias gradients (column sums of the dZ units in shared memory).
-//  3. tc_finish_kernel -- the weight gradients of `features` and of the first 256 rows of `rgb_features` from
-//     X = h7^T dG (tc_layout.cuh), a 256 x 256 x 128 problem once per call.
+//  3. tc_finish_kernel -- every gradient that contains d(rgb_features) = d(rgb_pre) Wc^T (rank 3): features,
+//     rgb_features and rgb kernels / biases from Y = h7^T d(rgb_pre), Yd = PE(dir)^T d(rgb_pre), sum d(rgb_pre).
 #include "mlp_tc.cuh"
 
 #include <cstdlib>
@@ -95,14 +95,15 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
   } else if (warp == 11) {
     if (lane == 0 && cta == 0) mma2_role<BwdProg>(sm, tmem, 1u, true, n_pairs, first, stride);
   } else if (warp == 10) {
-    // record store: every A operand of the chain is also a dZ record for the weight-gradient kernel -- item 0 = dG
-    // (prologue, 128 columns), items 1..7 = dZ7..dZ1 (tc_roles.cuh store_role)
+    // record store: the A operands dZ7..dZ1 of the chain (items 1..7) are also the dZ records of the weight-gradient
+    // kernel (tc_roles.cuh store_role); item 0 = dG only takes part in the hand-shake: nothing downstream reads it
+    // from HBM (its weight gradients factor through d(rgb_pre), see build_task_table)
     if (lane == 0) {
       store_role(sm, 8, n_tiles, n_pairs, first, stride, tile_of,
                  [&](int item, int64_t tile) {
                    return dz + tile * kDzBytes + (item == 0 ? kDzG : kDzZ0 + (8 - item) * kHSBytes);
                  },
-                 [](int item) { return (uint32_t)(item == 0 ? 32768 : kHSBytes); });
+                 [](int item) { return (uint32_t)(item == 0 ? 0 : kHSBytes); });   // dG stays on chip (item 0)
     }
   } else {
     uint32_t st_pending = 0, st_par = 0;      // bit tl = hs[tl] is being stored / parity of st_done[tl]
@@ -233,6 +234,10 @@ constexpr int kWUnitBytes = 32768;     // 16 chunks x 128 samples x 16 B: 128 fe
 constexpr int kWSlots = 7;            // 7 x 32 KB in flight per CTA (224 KB of the 227 KB)
 constexpr int kWThreads = 224;         // warp 0 producer, warps 1 and 6 MMA issuers, warps 2-5 flush
 constexpr int kNumTasks = 10;
+// Item share of the heads task (a `big` task is 128).  It moves only 76 KB per tile but issues 24 N = 16 MMAs, each of
+// which holds its issuing thread as long as a wide one: measured 2.08 / 1.76 / 1.65 / 1.65 / 1.63 ns per sample for
+// the whole kernel at 50 / 80 / 110 / 140 / 178; 178 gives 217 + 36 + 43 = 296 items = exactly two per CTA.
+constexpr int kHeadsCost = 178;
 constexpr int kWMaxUnits = 6;
 
 // one ring slot: `bytes` from the forward (src 0) or dz (src 1) record at offset 0 and, optionally, `bytes2` from the
@@ -243,10 +248,10 @@ struct WUnit { int src, off, bytes, bias_layer, bias_col0, off2, bytes2; };
 struct WGroup { int a, b, col, N, layer, row_base, row_limit, col_base, mode, free_a, free_b, a_sub, b_sub, issuer; };
 // last_grp[x][k]: the last group of issuer x that reads unit k (the one after which x releases the slot), -1 = none
 struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUnits]; int cost; int8_t last_grp[2][kWMaxUnits]; };
-// mode 0: dW[layer][(row_base+row), col_base+col]   1: sigma kernel (column 3 of the d_pre operand)   2: rgb kernel
-//      3: X = h7^T dG into the fp32 scratch (tc_finish_kernel turns it into dW_features and dW_rgb_features[:256])
-//      4: Yd = PE(dir)^T d(rgb_pre) into the scratch (columns 0..2 of the d_pre operand; rgb kernel, tc_finish_kernel)
-// (mode 1 groups also leave Y = h7^T d(rgb_pre), columns 0..2 of the same accumulator, in the scratch)
+// mode 0: dW[layer][(row_base+row), col_base+col]
+//      1: A = h7, B = the packed d_pre operand: column 3 = the sigma kernel's gradient, columns 0..2 = Y = h7^T d(rgb_pre)
+//         into the fp32 scratch
+//      4: A = PE(dir): columns 0..2 = Yd = PE(dir)^T d(rgb_pre) into the scratch     (tc_finish_kernel uses Y, Yd)
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
@@ -283,28 +288,26 @@ static WTaskTable build_task_table() {
   xpart(0, kDzZ0, 0);                                                        // layer 0
   for (int l = 1; l <= 7; ++l) big(l, kRecH0 + (l - 1) * kHSBytes, kDzZ0 + l * kHSBytes, 0);   // layers 1..7 (h part)
   xpart(5, kDzZ0 + 5 * kHSBytes, 256);                                       // layer 5, skip rows 256..318
-  {  // everything that hangs off h7 and d(rgb_features): h7 is read ONCE for X = h7^T dG (-> features and
-     // rgb_features[:256], tc_finish_kernel) and for the sigma kernel; the direction rows of rgb_features and the
-     // rgb kernel (A = rgb_features activations, B = the packed d_pre operand, N = 16) ride along.
-     // Units in order of first use; groups ordered so that each unit is released as early as possible.
+  {  // Everything that hangs off h7 and d(rgb_features).  d(rgb_features) = dG = d(rgb_pre) Wc^T has rank 3, so every
+     // gradient that contains it factors through three columns:  h7^T dG = (h7^T d(rgb_pre)) Wc^T,
+     // PE(dir)^T dG = (PE(dir)^T d(rgb_pre)) Wc^T,  sum dG = (sum d(rgb_pre)) Wc^T.  The task therefore reads h7, PE(dir)
+     // and the packed (d rgb_pre, d sigma_pre) operand only -- N = 16 MMAs -- and leaves Y = h7^T d(rgb_pre) [256 x 3]
+     // (+ the sigma kernel's gradient, column 3 of the same accumulator), Yd = PE(dir)^T d(rgb_pre) [27 x 3] and
+     // s3 = sum d(rgb_pre) in the scratch; tc_finish_kernel expands them into dW / db of features, rgb_features and
+     // rgb.  Neither dG nor the rgb_features activations travel through HBM (64 KB per tile less than round 1).
     WTask& t = T.t[n++];
     const int h7 = kRecH0 + 7 * kHSBytes;
-    t.n_units = 4;
+    t.n_units = 3;
     t.u[0] = {0, h7, kWUnitBytes, -1, 0, 0, 0};                 // h7 features 0..127
-    t.u[1] = {1, kDzG, kWUnitBytes, 10, 0, 0, 0};               // dG (its column sums = db_rgb_features)
-    t.u[2] = {0, kRecDS, 8192, -1, 0, kDzP, 4096};              // PE(dir) (32 columns, 27 valid accumulator rows) and,
+    t.u[1] = {0, kRecDS, 8192, -1, 0, kDzP, 4096};              // PE(dir) (32 columns, 27 valid accumulator rows) and,
                                                                 // at +8192, the packed (d rgb_pre, d sigma_pre) operand
-    t.u[3] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0, 0, 0};   // h7 features 128..255
-    t.n_groups = 6;
-    t.g[0] = {0, 1, 0, 128, -1, 0, 128, 0, 3, 0, 0, 0, 0};
-    t.g[1] = {0, 2, 384, 16, 8, 0, 128, 0, 1, 1, 0, 0, 8192};   // sigma kernel (column 3) + Y rows 0..127 (columns 0..2)
-    t.g[2] = {3, 1, 128, 128, -1, 128, 128, 0, 3, 0, 0, 0, 0};
-    t.g[3] = {3, 2, 400, 16, 8, 128, 128, 0, 1, 1, 0, 0, 8192};
-    t.g[4] = {2, 1, 256, 128, 10, 256, 27, 0, 0, 0, 1, 0, 0};
-    t.g[5] = {2, 2, 416, 16, -1, 0, 27, 0, 4, 1, 1, 0, 8192};   // Yd = PE(dir)^T d(rgb_pre): A and B share the unit
-    t.cost = 170;
-    // the three N = 128 groups are the heavy ones: two on issuer 0, the third with the three N = 16 groups on issuer 1
-    t.g[0].issuer = 0; t.g[2].issuer = 0; t.g[1].issuer = 1; t.g[3].issuer = 1; t.g[4].issuer = 1; t.g[5].issuer = 1;
+    t.u[2] = {0, h7 + kWUnitBytes, kWUnitBytes, -1, 0, 0, 0};   // h7 features 128..255
+    t.n_groups = 3;
+    t.g[0] = {0, 1, 0, 16, 8, 0, 128, 0, 1, 0, 0, 0, 8192};     // Y rows 0..127 (columns 0..2), sigma kernel (column 3)
+    t.g[1] = {2, 1, 32, 16, 8, 128, 128, 0, 1, 0, 0, 0, 8192};  // rows 128..255
+    t.g[2] = {1, 1, 64, 16, -1, 0, 27, 0, 4, 0, 0, 0, 8192};    // Yd: A and B share the unit
+    t.g[0].issuer = 0; t.g[1].issuer = 1; t.g[2].issuer = 0;
+    t.cost = kHeadsCost;
   }
   // Two MMA-issuing threads (tcgen05.mma holds its issuer for ~160 cycles per N = 128 MMA whose pipe time is 64):
   // every accumulator group belongs to ONE issuer, so the fp32 accumulation order of each gradient element -- and
@@ -500,10 +503,6 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + fc * 8;
 #pragma unroll
             for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e]);
-            if (t.u[k].bias_layer == 10) {   // sum(dG) of THIS call, for tc_finish_kernel
-#pragma unroll
-              for (int e = 0; e < 8; ++e) atomicAdd(xbuf + 256 * 128 + t.u[k].bias_col0 + fc * 8 + e, a[e]);
-            }
           }
           ++nb;
         }
@@ -530,10 +529,6 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               float* dst = grads + P.w_off[g.layer] + (int64_t)(g.row_base + row) * ld + g.col_base + c0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
-            } else if (g.mode == 3) {
-              float* dst = xbuf + (int64_t)(g.row_base + row) * 128 + c0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
             } else if (g.mode == 1) {
               atomicAdd(grads + P.w_off[8] + g.row_base + row, v[3]);
               float* dst = xbuf + kXOffY + (g.row_base + row) * 4;
@@ -555,50 +550,84 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 }
 
 // =============================================================================================================
-// features / rgb_features weight gradients from X = h7^T dG (tc_layout.cuh)
+// heads: features / rgb_features / rgb gradients from the rank-3 factors
 // =============================================================================================================
-//   dW_f[i][j]      += sum_n X[i][n] W_g[j][n]                         (i, j < 256; W_g = rgb_features kernel [283,128])
-//   dW_g[j][n]      += sum_i W_f[i][j] X[i][n] + b_f[j] s[n]           (j < 256, n < 128; s = sum(dG) of this call)
-//   db_f[j]         += sum_n s[n] W_g[j][n]
-// One thread per output element; 12.6 M MAC per call, operands (384 KB) stay in L2.
-//   dW_c[k][c]      += sum_j W'[j][k] Y[j][c] + sum_i W_g[256+i][k] Yd[i][c] + b'[k] s3[c]     (k < 128, c < 3: the rgb kernel;
-//                      G^T d(rgb_pre) with G = h7 W' + PE(dir) W_g[256:] + b', Y = h7^T d(rgb_pre), Yd = PE(dir)^T d(rgb_pre),
-//                      s3 = sum d(rgb_pre); `fold` = the fp32 W' [256,128] and b' [128] of the packed weights)
+// With Y = h7^T d(rgb_pre) [256 x 3], Yd = PE(dir)^T d(rgb_pre) [27 x 3], s3 = sum d(rgb_pre) [3] of THIS call (scratch,
+// 4 floats per row) and the weights W_f [256,256], b_f, W_g [283,128], W_c [128,3], W' = W_f W_g[:256], b' (fold):
+//   X = h7^T dG = Y W_c^T,  sum dG = s3 W_c^T   (never formed: T[j][c] = sum_n W_g[j][n] W_c[n][c],
+//                                                U[j][c] = sum_i W_f[i][j] Y[i][c] + b_f[j] s3[c])
+//   dW_f[i][j]        += sum_c Y[i][c] T[j][c]                    db_f[j]  += sum_c s3[c] T[j][c]
+//   dW_g[j][n]        += sum_c U[j][c] W_c[n][c]      (j < 256)   db_g[n]  += sum_c s3[c] W_c[n][c]
+//   dW_g[256 + i][n]  += sum_c Yd[i][c] W_c[n][c]     (i < 27)
+//   dW_c[k][c]        += sum_j W'[j][k] Y[j][c] + sum_i W_g[256+i][k] Yd[i][c] + b'[k] s3[c]
+// One thread per output element, the small factors recomputed per thread (50 M MAC per call, operands in L2).
+constexpr int kFinF = 256 * 256, kFinG = 256 * 128, kFinBf = 256, kFinGd = 27 * 128, kFinBg = 128, kFinC = 128 * 3;
+constexpr int kFinTotal = kFinF + kFinG + kFinBf + kFinGd + kFinBg + kFinC;
+
 __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict__ params, TcParams P,
                                                         const float* __restrict__ xbuf, float* __restrict__ grads,
                                                         const float* __restrict__ fold) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* Wf = params + P.w_off[9];
-  const float* Wg = params + P.w_off[10];
-  const float* s = xbuf + 256 * 128;
-  if (idx < 256 * 256) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* Wf = params + P.w_off[9];    // features      [256, 256]
+  const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
+  const float* Wc = params + P.w_off[11];   // rgb           [128, 3]
+  const float* Y = xbuf + kXOffY;
+  const float* Yd = xbuf + kXOffYd;
+  const float s3[3] = {xbuf[kXOffS], xbuf[kXOffS + 1], xbuf[kXOffS + 2]};
+  auto Tj = [&](int j, float (&t)[3]) {      // T[j][c] = sum_n W_g[j][n] W_c[n][c]
+    t[0] = t[1] = t[2] = 0.f;
+    const float* w = Wg + j * 128;
+#pragma unroll 4
+    for (int n = 0; n < 128; ++n) {
+      const float g = w[n];
+      t[0] = fmaf(g, Wc[n * 3], t[0]); t[1] = fmaf(g, Wc[n * 3 + 1], t[1]); t[2] = fmaf(g, Wc[n * 3 + 2], t[2]);
+    }
+  };
+  if (idx < kFinF) {
     const int i = idx >> 8, j = idx & 255;
-    const float* x = xbuf + i * 128;
-    const float* w = Wg + j * 128;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int n = 0; n < 128; ++n) acc = fmaf(x[n], w[n], acc);
-    grads[P.w_off[9] + idx] += acc;
-  } else if (idx < 256 * 256 + 256 * 128) {
-    const int e = idx - 256 * 256, j = e >> 7, n = e & 127;
-    float acc = params[P.b_off[9] + j] * s[n];
-#pragma unroll 8
-    for (int i = 0; i < 256; ++i) acc = fmaf(Wf[i * 256 + j], xbuf[i * 128 + n], acc);
-    grads[P.w_off[10] + e] += acc;
-  } else if (idx < 256 * 256 + 256 * 128 + 256) {
-    const int j = idx - (256 * 256 + 256 * 128);
-    const float* w = Wg + j * 128;
-    float acc = 0.f;
-    for (int n = 0; n < 128; ++n) acc = fmaf(s[n], w[n], acc);
-    grads[P.b_off[9] + j] += acc;
-  } else if (idx < 256 * 256 + 256 * 128 + 256 + 128 * 3) {
-    const int e = idx - (256 * 256 + 256 * 128 + 256), k = e / 3, c = e - k * 3;
-    const float* Y = xbuf + kXOffY;
-    const float* Yd = xbuf + kXOffYd;
-    float acc = fold[256 * 128 + k] * xbuf[kXOffS + c];
+    float t[3];
+    Tj(j, t);
+    grads[P.w_off[9] + idx] += Y[i * 4] * t[0] + Y[i * 4 + 1] * t[1] + Y[i * 4 + 2] * t[2];
+    return;
+  }
+  idx -= kFinF;
+  if (idx < kFinG) {
+    const int j = idx >> 7, n = idx & 127;
+    const float bf = params[P.b_off[9] + j];
+    float u[3] = {bf * s3[0], bf * s3[1], bf * s3[2]};
+#pragma unroll 4
+    for (int i = 0; i < 256; ++i) {
+      const float w = Wf[i * 256 + j];
+      u[0] = fmaf(w, Y[i * 4], u[0]); u[1] = fmaf(w, Y[i * 4 + 1], u[1]); u[2] = fmaf(w, Y[i * 4 + 2], u[2]);
+    }
+    grads[P.w_off[10] + idx] += u[0] * Wc[n * 3] + u[1] * Wc[n * 3 + 1] + u[2] * Wc[n * 3 + 2];
+    return;
+  }
+  idx -= kFinG;
+  if (idx < kFinBf) {
+    float t[3];
+    Tj(idx, t);
+    grads[P.b_off[9] + idx] += s3[0] * t[0] + s3[1] * t[1] + s3[2] * t[2];
+    return;
+  }
+  idx -= kFinBf;
+  if (idx < kFinGd) {
+    const int i = idx >> 7, n = idx & 127;
+    grads[P.w_off[10] + 256 * 128 + idx] += Yd[i * 4] * Wc[n * 3] + Yd[i * 4 + 1] * Wc[n * 3 + 1] + Yd[i * 4 + 2] * Wc[n * 3 + 2];
+    return;
+  }
+  idx -= kFinGd;
+  if (idx < kFinBg) {
+    grads[P.b_off[10] + idx] += s3[0] * Wc[idx * 3] + s3[1] * Wc[idx * 3 + 1] + s3[2] * Wc[idx * 3 + 2];
+    return;
+  }
+  idx -= kFinBg;
+  if (idx < kFinC) {
+    const int k = idx / 3, c = idx - k * 3;
+    float acc = fold[256 * 128 + k] * s3[c];
     for (int j = 0; j < 256; ++j) acc = fmaf(fold[j * 128 + k], Y[j * 4 + c], acc);
     for (int i = 0; i < 27; ++i) acc = fmaf(Wg[(256 + i) * 128 + k], Yd[i * 4 + c], acc);
-    grads[P.w_off[11] + e] += acc;
+    grads[P.w_off[11] + idx] += acc;
   }
 }
 
@@ -640,8 +669,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   }
   if (parts & 2) {
     static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
-    // items ~ 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 170 -> 217 + 36 + 41 = 294 items for 31 slabs
-    // (re-measured after the G record went away: heads cost 120 / 140 / 150 / 200 and 32 slabs x cost 136 are all slower)
+    // items = 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 178 -> 217 + 36 + 43 = 296 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
     const int grid = std::min(n_items, kNumSMs);
@@ -650,7 +678,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
     KN_LAUNCH_CHECK();
-    tc_finish_kernel<<<(256 * 256 + 256 * 128 + 256 + 128 * 3 + 255) / 256, 256, 0, st>>>(
+    tc_finish_kernel<<<(kFinTotal + 255) / 256, 256, 0, st>>>(
         params, P, xbuf, grads, reinterpret_cast<const float*>((const uint8_t*)packed + kFoldOff));
     KN_LAUNCH_CHECK();
   }

@@ -125,12 +125,13 @@ constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns 
 constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 576 KB per 128 samples
 // pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
 constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB
-constexpr int kDzG = 8 * kHSBytes;                 // d rgb_features 32 KB
+constexpr int kDzG = 8 * kHSBytes;                 // (unused since round 2: d rgb_features stays on chip)
 constexpr int kDzP = kDzG + 32768;                 // (d rgb_pre[3], d sigma_pre, 0...) [2 chunks][128][8]  4 KB
 constexpr int kDzBytes = kDzP + 4096;              // 548 KB per 128 samples
-// fp32 scratch at the head of the training workspace: X = h7^T dG [256 x 128], sum(dG) [128], then for the rgb
-// kernel's gradient Y = h7^T d(rgb_pre) [256 x 4], Yd = PE(dir)^T d(rgb_pre) [32 x 4] and sum d(rgb_pre) [4]
-constexpr int kXOffY = 256 * 128 + 128;
+// fp32 scratch at the head of the training workspace (zeroed by every backward call): Y = h7^T d(rgb_pre) [256 x 4],
+// Yd = PE(dir)^T d(rgb_pre) [32 x 4] and sum d(rgb_pre) [4] -- the rank-3 factors of every gradient that contains
+// d(rgb_features) (tc_finish_kernel)
+constexpr int kXOffY = 0;
 constexpr int kXOffYd = kXOffY + 256 * 4;
 constexpr int kXOffS = kXOffYd + 32 * 4;
 constexpr int kXFloats = kXOffS + 4;
