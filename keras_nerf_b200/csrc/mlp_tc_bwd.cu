@@ -560,54 +560,57 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 //   dW_g[j][n]        += sum_c U[j][c] W_c[n][c]      (j < 256)   db_g[n]  += sum_c s3[c] W_c[n][c]
 //   dW_g[256 + i][n]  += sum_c Yd[i][c] W_c[n][c]     (i < 27)
 //   dW_c[k][c]        += sum_j W'[j][k] Y[j][c] + sum_i W_g[256+i][k] Yd[i][c] + b'[k] s3[c]
-// One thread per output element, the small factors recomputed per thread (50 M MAC per call, operands in L2).
+// tc_finish_prep_kernel forms T and U (256 x 3 each), tc_finish_kernel one output element per thread.
 constexpr int kFinF = 256 * 256, kFinG = 256 * 128, kFinBf = 256, kFinGd = 27 * 128, kFinBg = 128, kFinC = 128 * 3;
 constexpr int kFinTotal = kFinF + kFinG + kFinBf + kFinGd + kFinBg + kFinC;
+
+// the two 256 x 3 factors every output of tc_finish_kernel needs (one thread each; 0.3 M MAC)
+__global__ void __launch_bounds__(256) tc_finish_prep_kernel(const float* __restrict__ params, TcParams P,
+                                                             float* __restrict__ xbuf) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // < 2 * 256 * 3
+  const int which = idx / 768, e = idx - which * 768, j = e / 3, c = e - j * 3;
+  if (which > 1) return;
+  const float* Wc = params + P.w_off[11];
+  float acc;
+  if (which == 0) {
+    const float* w = params + P.w_off[10] + j * 128;
+    acc = 0.f;
+    for (int n = 0; n < 128; ++n) acc = fmaf(w[n], Wc[n * 3 + c], acc);
+    xbuf[kXOffT + j * 4 + c] = acc;
+  } else {
+    const float* Wf = params + P.w_off[9];
+    const float* Y = xbuf + kXOffY;
+    acc = params[P.b_off[9] + j] * xbuf[kXOffS + c];
+    for (int i = 0; i < 256; ++i) acc = fmaf(Wf[i * 256 + j], Y[i * 4 + c], acc);
+    xbuf[kXOffU + j * 4 + c] = acc;
+  }
+}
 
 __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict__ params, TcParams P,
                                                         const float* __restrict__ xbuf, float* __restrict__ grads,
                                                         const float* __restrict__ fold) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* Wf = params + P.w_off[9];    // features      [256, 256]
   const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
   const float* Wc = params + P.w_off[11];   // rgb           [128, 3]
   const float* Y = xbuf + kXOffY;
   const float* Yd = xbuf + kXOffYd;
+  const float* T = xbuf + kXOffT;
+  const float* U = xbuf + kXOffU;
   const float s3[3] = {xbuf[kXOffS], xbuf[kXOffS + 1], xbuf[kXOffS + 2]};
-  auto Tj = [&](int j, float (&t)[3]) {      // T[j][c] = sum_n W_g[j][n] W_c[n][c]
-    t[0] = t[1] = t[2] = 0.f;
-    const float* w = Wg + j * 128;
-#pragma unroll 4
-    for (int n = 0; n < 128; ++n) {
-      const float g = w[n];
-      t[0] = fmaf(g, Wc[n * 3], t[0]); t[1] = fmaf(g, Wc[n * 3 + 1], t[1]); t[2] = fmaf(g, Wc[n * 3 + 2], t[2]);
-    }
-  };
   if (idx < kFinF) {
     const int i = idx >> 8, j = idx & 255;
-    float t[3];
-    Tj(j, t);
-    grads[P.w_off[9] + idx] += Y[i * 4] * t[0] + Y[i * 4 + 1] * t[1] + Y[i * 4 + 2] * t[2];
+    grads[P.w_off[9] + idx] += Y[i * 4] * T[j * 4] + Y[i * 4 + 1] * T[j * 4 + 1] + Y[i * 4 + 2] * T[j * 4 + 2];
     return;
   }
   idx -= kFinF;
   if (idx < kFinG) {
     const int j = idx >> 7, n = idx & 127;
-    const float bf = params[P.b_off[9] + j];
-    float u[3] = {bf * s3[0], bf * s3[1], bf * s3[2]};
-#pragma unroll 4
-    for (int i = 0; i < 256; ++i) {
-      const float w = Wf[i * 256 + j];
-      u[0] = fmaf(w, Y[i * 4], u[0]); u[1] = fmaf(w, Y[i * 4 + 1], u[1]); u[2] = fmaf(w, Y[i * 4 + 2], u[2]);
-    }
-    grads[P.w_off[10] + idx] += u[0] * Wc[n * 3] + u[1] * Wc[n * 3 + 1] + u[2] * Wc[n * 3 + 2];
+    grads[P.w_off[10] + idx] += U[j * 4] * Wc[n * 3] + U[j * 4 + 1] * Wc[n * 3 + 1] + U[j * 4 + 2] * Wc[n * 3 + 2];
     return;
   }
   idx -= kFinG;
   if (idx < kFinBf) {
-    float t[3];
-    Tj(idx, t);
-    grads[P.b_off[9] + idx] += s3[0] * t[0] + s3[1] * t[1] + s3[2] * t[2];
+    grads[P.b_off[9] + idx] += s3[0] * T[idx * 4] + s3[1] * T[idx * 4 + 1] + s3[2] * T[idx * 4 + 2];
     return;
   }
   idx -= kFinBf;
@@ -677,6 +680,8 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     KN_CUDA(cudaMemsetAsync(xbuf, 0, kXFloats * sizeof(float), st));
     KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
+    KN_LAUNCH_CHECK();
+    tc_finish_prep_kernel<<<6, 256, 0, st>>>(params, P, xbuf);
     KN_LAUNCH_CHECK();
     tc_finish_kernel<<<(kFinTotal + 255) / 256, 256, 0, st>>>(
         params, P, xbuf, grads, reinterpret_cast<const float*>((const uint8_t*)packed + kFoldOff));

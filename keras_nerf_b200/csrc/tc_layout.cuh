@@ -134,7 +134,9 @@ constexpr int kDzBytes = kDzP + 4096;              // 548 KB per 128 samples
 constexpr int kXOffY = 0;
 constexpr int kXOffYd = kXOffY + 256 * 4;
 constexpr int kXOffS = kXOffYd + 32 * 4;
-constexpr int kXFloats = kXOffS + 4;
+constexpr int kXOffT = kXOffS + 4;           // T[j][c] = sum_n W_g[j][n] W_c[n][c]                      [256 x 4]
+constexpr int kXOffU = kXOffT + 256 * 4;     // U[j][c] = sum_i W_f[i][j] Y[i][c] + b_f[j] s3[c]            [256 x 4]
+constexpr int kXFloats = kXOffU + 256 * 4;   // (T, U: written by tc_finish_prep_kernel, read by tc_finish_kernel)
 constexpr int kXBytes = ((kXFloats * 4 + 255) / 256) * 256;
 
 struct ChainSmem {
