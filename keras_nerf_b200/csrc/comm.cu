@@ -50,6 +50,8 @@ const NcclApi* nccl_api() {
 
 }  // namespace
 
+extern "C" int knerf_comm_destroy(knerf_comm* comm);
+
 struct knerf_comm {
   ncclComm_t nccl;
   int rank, nranks;
@@ -69,8 +71,14 @@ namespace knerf {
 static int make_comm(ncclComm_t nccl, int rank, int nranks, bool owned, knerf_comm** out) {
   knerf_comm* c = new (std::nothrow) knerf_comm{nccl, rank, nranks, owned, {nullptr, nullptr}, nullptr};
   if (c == nullptr) return fail(KNERF_ERR_INVALID, "out of host memory");
-  for (int i = 0; i < 2; ++i) KN_CUDA(cudaEventCreateWithFlags(&c->ready[i], cudaEventDisableTiming));
-  KN_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ready[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {   // nothing half-built escapes: the caller gets no handle
+    c->owned = owned;
+    knerf_comm_destroy(c);
+    return fail(KNERF_ERR_CUDA, "cudaEventCreateWithFlags failed: %s", cudaGetErrorString(e));
+  }
   *out = c;
   return KNERF_OK;
 }
