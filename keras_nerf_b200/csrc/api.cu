@@ -59,9 +59,11 @@ int build_model(const knerf_config* cfg, Model* m) {
   return KNERF_OK;
 }
 
+// the shapes the fused bf16 chain kernels implement: 8 x 256, skip 4, and encodings that are prefixes of PE_10 / PE_4
 bool is_flagship(const Model& m) {
-  return m.n_layers == 8 && m.U == 256 && m.cfg.skip_layer == 4 && m.dx == 63 && m.dd == 27 &&
-         m.cfg.pos_emb_xyz == 10 && m.cfg.pos_emb_dir == 4;
+  return m.n_layers == 8 && m.U == 256 && m.cfg.skip_layer == 4 && m.cfg.pos_emb_xyz >= 0 && m.cfg.pos_emb_xyz <= 10 &&
+         m.cfg.pos_emb_dir >= 0 && m.cfg.pos_emb_dir <= 4 && m.dx == 3 + 6 * m.cfg.pos_emb_xyz &&
+         m.dd == 3 + 6 * m.cfg.pos_emb_dir;
 }
 
 }  // namespace knerf

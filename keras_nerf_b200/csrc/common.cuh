@@ -141,6 +141,6 @@ struct Model {
 };
 
 int build_model(const knerf_config* cfg, Model* m);
-bool is_flagship(const Model& m);  // 8x256, skip 4, L 10/4: the shape the tcgen05 path implements
+bool is_flagship(const Model& m);  // 8 x 256, skip 4, L_xyz <= 10, L_dir <= 4: the shapes the fused bf16 path implements
 
 }  // namespace knerf

@@ -34,7 +34,7 @@ namespace {
 // B operand element of forward step s < 8 at reduction index k (hs part first, then the encoding part), output n
 __device__ __forceinline__ float fwd_weight(const float* __restrict__ params, const TcParams& P, int s, int k, int n) {
   const int L = s, kh = FwdProg::nk_h(s) * kKStage;
-  const int fan_in = (L == 0) ? 63 : (L == 5) ? 319 : 256;
+  const int fan_in = (L == 0) ? P.dx : (L == 5) ? 256 + P.dx : 256;
   const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
   return row < fan_in ? params[P.w_off[L] + (int64_t)row * 256 + n] : 0.f;
 }
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) fold_kernel(const float* __restrict__ par
 __device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P,
                                              const float* __restrict__ fold, int k, int n) {
   if (n < 128) {
-    if (k >= 256) return (k - 256 < 27) ? params[P.w_off[10] + (int64_t)k * 128 + n] : 0.f;
+    if (k >= 256) return (k - 256 < P.dd) ? params[P.w_off[10] + (int64_t)k * 128 + n] : 0.f;
     return fold[k * 128 + n];
   }
   return (n == 128 && k < 256) ? params[P.w_off[8] + k] : 0.f;   // sigma kernel [256, 1]
@@ -493,11 +493,13 @@ int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training) {
 TcParams tc_make_params(const Model& m) {
   TcParams P;
   for (int i = 0; i < 12; ++i) { P.w_off[i] = m.L[i].w_off; P.b_off[i] = m.L[i].b_off; }
+  P.dx = m.dx;
+  P.dd = m.dd;
   return P;
 }
 
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_weights: packed must be 16-byte aligned");
   fold_kernel<<<257, 128, 0, st>>>(params, tc_make_params(m), reinterpret_cast<float*>((uint8_t*)packed + kFoldOff));
   KN_LAUNCH_CHECK();
@@ -510,7 +512,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
                int64_t R, int S, bool training, bool ordered_issue, float* rgbsigma, char* ws, int64_t ws_bytes,
                cudaStream_t st) {
   (void)params;
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   const int64_t M = R * S;
   if (training && ws_bytes < tc_workspace_bytes(m, M, true))
     return fail(KNERF_ERR_WORKSPACE, "tc_forward: workspace %lld < %lld bytes", (long long)ws_bytes,

@@ -255,7 +255,7 @@ struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUni
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
-static WTaskTable build_task_table() {
+static WTaskTable build_task_table(int dx, int dd) {
   WTaskTable T{};
   int n = 0;
   auto big = [&](int layer, int a_off, int b_off, int row_base) {   // A: two 128-feature halves, B: two 128-output halves
@@ -279,8 +279,8 @@ static WTaskTable build_task_table() {
     t.u[0] = {0, kRecXS, kXSBytes, -1, 0}; t.u[1] = {1, b_off, kWUnitBytes, bl, 0};
     t.u[2] = {1, b_off + kWUnitBytes, kWUnitBytes, bl, 128};
     t.n_groups = 2;
-    t.g[0] = {0, 1, 0, 128, layer, row_base, 63, 0, 0, 0, 1};
-    t.g[1] = {0, 2, 128, 128, layer, row_base, 63, 128, 0, 1, 1};
+    t.g[0] = {0, 1, 0, 128, layer, row_base, dx, 0, 0, 0, 1};
+    t.g[1] = {0, 2, 128, 128, layer, row_base, dx, 128, 0, 1, 1};
     t.cost = 76;    // costs = measured time per tile of a CTA working alone on the task (x 128 / the `big` tasks'):
                     // 3,700 / 6,300 / 8,400 cycles -- the kernel is bound by its CTAs' per-tile time, so equal item
                     // TIMES (not bytes) remove the tail
@@ -305,7 +305,7 @@ static WTaskTable build_task_table() {
     t.n_groups = 3;
     t.g[0] = {0, 1, 0, 16, 8, 0, 128, 0, 1, 0, 0, 0, 8192};     // Y rows 0..127 (columns 0..2), sigma kernel (column 3)
     t.g[1] = {2, 1, 32, 16, 8, 128, 128, 0, 1, 0, 0, 0, 8192};  // rows 128..255
-    t.g[2] = {1, 1, 64, 16, -1, 0, 27, 0, 4, 0, 0, 0, 8192};    // Yd: A and B share the unit
+    t.g[2] = {1, 1, 64, 16, -1, 0, dd, 0, 4, 0, 0, 0, 8192};    // Yd: A and B share the unit
     t.g[0].issuer = 0; t.g[1].issuer = 1; t.g[2].issuer = 0;
     t.cost = kHeadsCost;
   }
@@ -561,7 +561,7 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 //   dW_g[256 + i][n]  += sum_c Yd[i][c] W_c[n][c]     (i < 27)
 //   dW_c[k][c]        += sum_j W'[j][k] Y[j][c] + sum_i W_g[256+i][k] Yd[i][c] + b'[k] s3[c]
 // tc_finish_prep_kernel forms T and U (256 x 3 each), tc_finish_kernel one output element per thread.
-constexpr int kFinF = 256 * 256, kFinG = 256 * 128, kFinBf = 256, kFinGd = 27 * 128, kFinBg = 128, kFinC = 128 * 3;
+constexpr int kFinF = 256 * 256, kFinG = 256 * 128, kFinBf = 256, kFinGd = 27 * 128, kFinBg = 128, kFinC = 128 * 3;   // (kFinGd: rows >= dd idle)
 constexpr int kFinTotal = kFinF + kFinG + kFinBf + kFinGd + kFinBg + kFinC;
 
 // the two 256 x 3 factors every output of tc_finish_kernel needs (one thread each; 0.3 M MAC)
@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
   idx -= kFinBf;
   if (idx < kFinGd) {
     const int i = idx >> 7, n = idx & 127;
-    grads[P.w_off[10] + 256 * 128 + idx] += Yd[i * 4] * Wc[n * 3] + Yd[i * 4 + 1] * Wc[n * 3 + 1] + Yd[i * 4 + 2] * Wc[n * 3 + 2];
+    if (i < P.dd)
+      grads[P.w_off[10] + 256 * 128 + idx] += Yd[i * 4] * Wc[n * 3] + Yd[i * 4 + 1] * Wc[n * 3 + 1] + Yd[i * 4 + 2] * Wc[n * 3 + 2];
     return;
   }
   idx -= kFinGd;
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
     const int k = idx / 3, c = idx - k * 3;
     float acc = fold[256 * 128 + k] * s3[c];
     for (int j = 0; j < 256; ++j) acc = fmaf(fold[j * 128 + k], Y[j * 4 + c], acc);
-    for (int i = 0; i < 27; ++i) acc = fmaf(Wg[(256 + i) * 128 + k], Yd[i * 4 + c], acc);
+    for (int i = 0; i < P.dd; ++i) acc = fmaf(Wg[(256 + i) * 128 + k], Yd[i * 4 + c], acc);
     grads[P.w_off[11] + idx] += acc;
   }
 }
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
 // parts: which of the backward kernels to launch (bit 0 dgrad, bit 1 wgrad + finish; KNERF_BWD_*_ONLY)
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, int parts, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8x256 / skip 4 / L=10,4 model only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
   if (ws_bytes < tc_workspace_bytes(m, M, true))
@@ -671,7 +672,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     KN_LAUNCH_CHECK();
   }
   if (parts & 2) {
-    static const WTaskTable h_table = build_task_table();   // ~4 KB, passed by value as a __grid_constant__
+    const WTaskTable h_table = build_task_table(m.dx, m.dd);   // ~3 KB, passed by value as a __grid_constant__
     // items = 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 178 -> 217 + 36 + 43 = 296 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);

@@ -109,6 +109,10 @@ constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
 
 struct TcParams {
   int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
+  int dx, dd;                     // widths of the encodings the model uses: 3 + 6 L_xyz <= 63, 3 + 6 L_dir <= 27.  PE_L is a
+                                  // prefix of PE_10 / PE_4 (utils.py:176-186 appends one sin / cos block per frequency), so a
+                                  // model with fewer frequencies runs on the same kernels: the operand keeps all 63 / 27
+                                  // columns, the packed weights of the unused ones are zero and their gradients are not flushed
 };
 
 // ---- per-tile records in the training workspace (chunk-major bf16) -------------------------------------------

@@ -160,6 +160,29 @@ def test_bf16_request_on_other_shape_falls_back_loudly(caplog):
     assert all(np.isfinite(l["fine_loss"]) for l in logs) and logs[2]["coarse_loss"] != logs[0]["coarse_loss"]
 
 
+def test_bf16_train_step_with_fewer_encoding_frequencies():
+    """--pos_emb_xyz 6 --pos_emb_dir 2 stays on the fused bf16 kernels (no fall-back) through the whole train step and
+    tracks the fp32 mode's losses"""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    rng = np.random.default_rng(0)
+    pose = K.pose_spherical(10.0, -30.0, 4.0)
+    o, d, t = K.RaysGenerator(K.get_focal_from_fov(0.69, 32), 32, 16, 2.0, 6.0, 64)(pose, seed=3)
+    images = rng.uniform(0, 1, (1, 16, 32, 4)).astype(np.float32)
+    logs = {}
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(1)
+        m = K.NeRF(precision=prec, pos_emb_xyz=6, pos_emb_dir=2)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=16, image_width=32, ray_chunks=256,
+                  white_background=True)
+        assert m.precision == prec
+        logs[prec] = [m.train_step((images, (o[None], d[None], t[None])), seed=5 + i) for i in range(3)]
+    for a, b in zip(logs["fp32"], logs["bf16"]):
+        for k in ("coarse_loss", "fine_loss"):
+            assert abs(a[k] - b[k]) <= 2e-2 * abs(a[k]) + 1e-4, (k, a[k], b[k])
+    assert logs["bf16"][2]["coarse_loss"] != logs["bf16"][0]["coarse_loss"]
+
+
 def test_custom_loss_is_refused_and_initializers_accepted():
     import keras_nerf_b200 as K
     m = K.NeRF(precision="fp32")

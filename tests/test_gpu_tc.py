@@ -300,3 +300,105 @@ def test_tc_full_size_step_properties():
         assert torch.isfinite(im).all() and float(im.min()) >= 0.0 and float(im.max()) <= 1.0
         assert w.shape[-1] == S and float(w.min()) >= 0.0 and float(w.sum(-1).max()) <= 1.0 + 1e-4
         assert float(dep.min()) >= 0.0 and float(dep.max()) <= 6.0 + 1e-3
+
+
+@pytest.mark.parametrize("Lx,Ld", [(6, 2), (10, 0), (0, 4)])
+def test_tc_fewer_encoding_frequencies(Lx, Ld):
+    """--pos_emb_xyz / --pos_emb_dir below the defaults (train.py:24-25): PE_L is a prefix of PE_10 / PE_4, so the fused
+    bf16 kernels run such a model unchanged -- the packed weights of the unused encoding columns are zero and their
+    gradient rows are not flushed.  Forward and weight gradients against the fp32 mode, as for the default model."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S = 1031, 192
+    ms = []
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec, pos_emb_xyz=Lx, pos_emb_dir=Ld)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == prec                       # no fall-back: the bf16 kernels take this shape
+        ms.append(m)
+    m32, m16 = ms
+    assert torch.equal(m32.fine.params, m16.fine.params)
+    o, d, t, tgt = _rays(R, S, seed=3 + Lx)
+    grads, outs = {}, {}
+    for m in ms:
+        out = _fwd(m, m.fine, o, d, t, True)
+        outs[m.precision] = out
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        grads[m.precision] = gbuf.cpu()
+    ia, ib = _composite(outs["fp32"], t), _composite(outs["bf16"], t)
+    assert float((ia - ib).abs().max()) <= 2e-3
+    cfg = O.NerfConfig(pos_emb_xyz=Lx, pos_emb_dir=Ld)
+    a, b = grads["fp32"], grads["bf16"]
+    assert a.numel() == O.param_count(cfg)
+    # bf16 rounding noise, 1/sqrt(samples) as for the default model, but relative to gradients that cancel more when the
+    # encoding has fewer frequencies (measured at 1,024 rays: layer_0 kernel 0.012 for L = 10,4 and 0.043 for L = 6,2,
+    # falling to 0.005 at the heads; twice those at 257 rays)
+    tol = 8e-2
+    off = 0
+    for name, fi, fo in O.layer_shapes(cfg):
+        for n in (fi * fo, fo):
+            x, y = a[off:off + n], b[off:off + n]
+            assert float((x - y).norm() / x.norm().clamp_min(1e-30)) <= tol, name
+            off += n
+
+
+@pytest.mark.parametrize("Lx,Ld", [(6, 2), (3, 0)])
+def test_tc_fewer_frequencies_equal_zero_padded_default_model(Lx, Ld):
+    """Structure check of the same generalisation, free of rounding noise: a model with L_xyz, L_dir frequencies IS the
+    default model whose kernels have zero rows for the remaining encoding columns -- the bf16 forward output must be
+    bit-identical and the gradients of the shared rows equal up to the order of the atomic flushes."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S = 300, 192
+    mlp_mod.set_seed(7)
+    small = K.NeRF(precision="bf16", pos_emb_xyz=Lx, pos_emb_dir=Ld)
+    big = K.NeRF(precision="bf16")
+    for m in (small, big):
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == "bf16"
+    cs, cb = O.NerfConfig(pos_emb_xyz=Lx, pos_emb_dir=Ld), O.NerfConfig()
+    ps = small.fine.params.cpu()
+    # bias of every layer made non-zero so its gradient path is exercised too
+    ps = ps + 0.01 * torch.randn(ps.numel(), generator=torch.Generator().manual_seed(1))
+    pb = torch.zeros(O.param_count(cb))
+    rows = []                                            # (offset in small, offset in big, shared elements)
+    os_, ob = 0, 0
+    for (name, fs, fo), (_, fb, _) in zip(O.layer_shapes(cs), O.layer_shapes(cb)):
+        ks, kb = ps[os_:os_ + fs * fo].view(fs, fo), pb[ob:ob + fb * fo].view(fb, fo)
+        kb[:fs] = ks                                     # encoding rows come last ([hidden | PE], mlp.py:36-38, 51-52)
+        rows.append((os_, ob, fs * fo))                  # and PE_L is a prefix of PE_10 / PE_4
+        os_, ob = os_ + fs * fo, ob + fb * fo
+        pb[ob:ob + fo] = ps[os_:os_ + fo]
+        rows.append((os_, ob, fo))
+        os_, ob = os_ + fo, ob + fo
+    assert os_ == ps.numel() and ob == pb.numel()
+    small.fine.params.copy_(ps.to(small.fine.params.device))
+    big.fine.params.copy_(pb.to(big.fine.params.device))
+    small._repack()
+    big._repack()
+    o, d, t, tgt = _rays(R, S, seed=11)
+    res = []
+    for m in (small, big):
+        out = _fwd(m, m.fine, o, d, t, True)
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        res.append((out.cpu(), gbuf.cpu()))
+    (out_s, g_s), (out_b, g_b) = res
+    assert torch.equal(out_s, out_b)
+    for a, b, n in rows:
+        x, y = g_s[a:a + n], g_b[b:b + n]
+        assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-12, (a, b, n)
