@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time the tcgen05 MLP kernels alone (CUDA events on the launching stream): forward (inference / training),
-dgrad, wgrad.  usage: python benchmarks/tc_kernels.py [rays=8192] [samples_per_ray=192] [iters=10]"""
+dgrad, wgrad.  usage: python benchmarks/tc_kernels.py [rays=8192] [samples_per_ray=192] [iters=10] [records=bf16|fp8]"""
 import ctypes as C
 import json
 import os
@@ -20,11 +20,12 @@ def main():
     R = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 192
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+    records = sys.argv[4] if len(sys.argv) > 4 else "bf16"
     from keras_nerf_b200 import NeRF, _lib
     from keras_nerf_b200.model.nerf import mlp as mlp_mod
     dev = torch.device("cuda", 0)
     mlp_mod.set_seed(42)
-    model = NeRF(precision="bf16", device=dev, n_coarse=64, n_fine=S - 64)
+    model = NeRF(precision="bf16", device=dev, n_coarse=64, n_fine=S - 64, records=records)
     model.compile(optimizer="adam", loss="mse", batch_size=1, image_height=R // 64, image_width=64, ray_chunks=R,
                   white_background=True)
     rows = R * S
@@ -36,7 +37,7 @@ def main():
     rgbs = torch.empty(R, S, 4, device=dev)
     dpre = (torch.randn(R, S, 4, generator=g) * 1e-4).to(dev)
     grads = torch.zeros_like(model.fine.params)
-    prec = model._prec
+    prec = model._prec_train
     packed = model._packed_ptr("fine")
     ws, wsn = model._ws.data_ptr(), model._ws.numel()
     lib = _lib.load()
@@ -49,7 +50,7 @@ def main():
         _lib.call("knerf_mlp_backward", C.byref(model.cfg), _lib.ptr(model.fine.params), packed, _lib.ptr(dpre), R, S,
                   prec | flags, _lib.ptr(grads), ws, wsn, _lib.stream())
 
-    out = {"rays": R, "samples_per_ray": S, "rows": rows}
+    out = {"rays": R, "samples_per_ray": S, "rows": rows, "records": records}
 
     def rec(name, ms, flop):
         out[name] = {"ms": round(ms, 4), "tflops": round(flop * rows / ms / 1e9, 1), "ns_per_sample": round(ms * 1e6 / rows, 4)}

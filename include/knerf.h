@@ -70,11 +70,17 @@ typedef enum knerf_precision {
  *                       order like the training kernels do (bit-reproducible outputs, ~14 % slower).  Default:
  *                       they interleave freely (last-bit run-to-run differences).
  *  KNERF_BWD_DGRAD_ONLY / KNERF_BWD_WGRAD_ONLY   knerf_mlp_backward (BF16) launches only its dgrad chain kernel /
- *                       only its weight-gradient kernels, so that a benchmark can time them apart.            */
+ *                       only its weight-gradient kernels, so that a benchmark can time them apart.
+ *  KNERF_REC_FP8        BF16 training: the records the forward and the dgrad chain save for the weight-gradient GEMMs
+ *                       are 8-bit floats (activations e4m3, pre-activation gradients e5m2 under one power-of-two scale
+ *                       per backward call) instead of bf16: half the bytes through HBM, the forward outputs and the
+ *                       dgrad chain unchanged.  The training forward and the backward of a step must both carry it
+ *                       (knerf_train_chunk passes it to both).                                                  */
 #define KNERF_PRECISION_MASK 0xff
 #define KNERF_TC_ORDERED 0x100
 #define KNERF_BWD_DGRAD_ONLY 0x200
 #define KNERF_BWD_WGRAD_ONLY 0x400
+#define KNERF_REC_FP8 0x800
 
 /* The 7 ints of model_config.json (keras_nerf/model/nerf/nerf.py:47-55) + encoded widths.
  * dx/dd = width of the xyz / direction encodings fed to the MLP; 0 means 3+6*pos_emb_*.      */

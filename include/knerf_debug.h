@@ -12,7 +12,8 @@ extern "C" {
 
 /* One tcgen05 tile, D[128,N] (fp32, row-major) = A[128,K] * B[N,K]^T from bf16 operand blobs in the library's
  * chunk-major layout ([K/8][rows][8] for mode 0 = K-major; [rows/8][K][8] for mode 1 = MN-major, the
- * weight-gradient form). */
+ * weight-gradient form).  mode 2: the MN-major form over fp8 blobs [rows/16][K][16], A = e4m3, B = e5m2
+ * (kind::f8f6f4, K = 32 per instruction) -- the weight-gradient GEMM over fp8 records. */
 int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
                         void* stream);
 

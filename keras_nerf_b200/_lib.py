@@ -19,7 +19,7 @@ OOB_ZERO, OOB_CLAMP, OOB_COUNT = 0, 1, 2
 SCAN_SEQUENTIAL = 0x10   # OR-ed into oob_mode: pdf/cdf summed left to right (TF-CPU / NumPy order)
 FP32, BF16, FP32_TC = 0, 1, 2
 # per-call option bits OR-ed into `precision` (include/knerf.h)
-PRECISION_MASK, TC_ORDERED, BWD_DGRAD_ONLY, BWD_WGRAD_ONLY = 0xFF, 0x100, 0x200, 0x400
+PRECISION_MASK, TC_ORDERED, BWD_DGRAD_ONLY, BWD_WGRAD_ONLY, REC_FP8 = 0xFF, 0x100, 0x200, 0x400, 0x800
 COMM_ID_BYTES = 128
 PRECISIONS = {"fp32": FP32, "float32": FP32, "bf16": BF16, "bfloat16": BF16, "fp32_tc": FP32_TC, "fp32tc": FP32_TC}
 OOB_MODES = {"zero": OOB_ZERO, "clamp": OOB_CLAMP, "raise": OOB_COUNT}

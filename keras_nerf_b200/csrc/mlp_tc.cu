@@ -156,6 +156,8 @@ __device__ __forceinline__ void angle_double(float (&sn)[3], float (&cs)[3]) {
   }
 }
 
+// (REC8: the record is fp8 -- 16 columns per 16-byte vector, chunk index = chunk0 / 2 -- the operand stays bf16)
+template <bool REC8>
 __device__ __forceinline__ void store_cols(uint8_t* xs, uint8_t* rec, int r, int chunk0, const float* v, int nchunks) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -164,7 +166,18 @@ __device__ __forceinline__ void store_cols(uint8_t* xs, uint8_t* rec, int r, int
                                   pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
       const int off = (chunk0 + k) * kChunkA + r * 16;
       *reinterpret_cast<uint4*>(xs + off) = pk;
-      if (rec) *reinterpret_cast<uint4*>(rec + off) = pk;
+      if (!REC8 && rec) *reinterpret_cast<uint4*>(rec + off) = pk;
+    }
+  }
+  if (REC8 && rec) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (2 * k < nchunks) {
+        const float* x = v + 16 * k;
+        const uint4 q = make_uint4(pack_e4m3x4(x[0], x[1], x[2], x[3]), pack_e4m3x4(x[4], x[5], x[6], x[7]),
+                                   pack_e4m3x4(x[8], x[9], x[10], x[11]), pack_e4m3x4(x[12], x[13], x[14], x[15]));
+        __stcs(reinterpret_cast<uint4*>(rec + ((chunk0 >> 1) + k) * kChunkA + r * 16), q);
+      }
     }
   }
 }
@@ -195,6 +208,7 @@ __device__ __forceinline__ void load_dir(float (&x)[3], const float* __restrict_
   }
 }
 
+template <bool REC8>
 __device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, float px, float py, float pz) {
   const float p[3] = {px, py, pz};
   float sn[3], cs[3], v[34];
@@ -219,12 +233,13 @@ __device__ __noinline__ void pe_xyz(uint8_t* xs, uint8_t* rec, int r, int h, flo
     }
     v[31] = 1.f;
   }
-  store_cols(xs, rec, r, 4 * h, v, 4);
+  store_cols<REC8>(xs, rec, r, 4 * h, v, 4);
 }
 
 // PE_4(d) -> 27 columns, zeros in 27..30, the constant-1 column 31 (folded bias of steps 6..9) into chunks 0..3
 // of the xs buffer.  h = 0: columns 0..15 (identity, f = 0, 1, sin(4 x));  h = 1: columns 16..31.
 // (the record keeps only these 4 chunks: the weight-gradient kernel fetches 8 KB for this operand)
+template <bool REC8>
 __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, float x0, float x1, float x2) {
   const float x[3] = {x0, x1, x2};
   float sn[3], cs[3], v[18];
@@ -248,7 +263,7 @@ __device__ __noinline__ void pe_dir(uint8_t* xs, uint8_t* rec, int r, int h, flo
     v[11] = v[12] = v[13] = v[14] = 0.f;
     v[15] = 1.f;
   }
-  store_cols(xs, rec, r, 2 * h, v, 2);
+  store_cols<REC8>(xs, rec, r, 2 * h, v, 2);
 }
 
 // fp32 head weights staged in the dead half of a tile's encoding buffer: [0,256) sigma kernel, [256,640) rgb
@@ -260,9 +275,11 @@ __device__ __forceinline__ float* head_smem(uint8_t* xs) { return reinterpret_ca
 // (folded into the GEMM), ReLU (mlp.py:33-34) is fused into the bf16 conversion.  mask_out (training): the ReLU'
 // bits of the tile, 1 bit per activation (tc_layout.cuh kRecMask) for the dgrad kernel.
 // (__noinline__: one body for all eight layers keeps the kernel below the I-cache thrash point.)
-template <bool TRAIN>
+// rec8 (fp8 records): the tile's saved activation record goes to HBM from here, 16 columns per 16-byte vector,
+// rounded from the fp32 accumulator -- no copy of the operand tile, no hand-shake with a store warp.
+template <bool TRAIN, bool REC8>
 __device__ __noinline__ void epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
-                                        uint8_t* __restrict__ mask_out) {
+                                        uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rec8) {
 #pragma unroll 1
   for (int gI = 0; gI < 4; ++gI) {
     const int col0 = h * 128 + gI * 32;
@@ -285,19 +302,31 @@ __device__ __noinline__ void epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs,
       *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
     }
     if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
+    if (TRAIN && REC8 && rec8 != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float* x = reinterpret_cast<const float*>(&v[16 * k]);
+        const uint4 q = make_uint4(pack_e4m3x4_relu(x[0], x[1], x[2], x[3]), pack_e4m3x4_relu(x[4], x[5], x[6], x[7]),
+                                   pack_e4m3x4_relu(x[8], x[9], x[10], x[11]),
+                                   pack_e4m3x4_relu(x[12], x[13], x[14], x[15]));
+        __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + k) * kChunkA + r * 16), q);
+      }
+    }
   }
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------
 // Launched as clusters of 2: the CTA pair shares every weight stage through cta_group::2 MMAs (tc_roles2.cuh); a
 // work unit is four tiles (two per CTA).
-template <bool TRAIN>
+template <bool TRAIN, bool REC8>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ o, const float* __restrict__ d,
                   const float* __restrict__ t, int64_t M, int S, float4* __restrict__ rgbsigma,
                   uint8_t* __restrict__ rec, int ordered) {
   using Prog = FwdProg;
   constexpr int kLast = Prog::kSteps - 1;
+  constexpr int kRB = REC8 ? kRec8Bytes : kRecBytes, kOffXS = REC8 ? kRec8XS : kRecXS, kOffDS = REC8 ? kRec8DS : kRecDS,
+                kOffMask = REC8 ? kRec8Mask : kRecMask;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -317,7 +346,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     if (lane == 0 && cta == 0) mma2_role<Prog>(sm, tmem, 1u, ordered != 0, n_pairs, first, stride);
   } else if (warp == 10) {
     // ============== record store (training): the operand tiles h0..h7 -> HBM, bulk copies ======================
-    if constexpr (TRAIN) {
+    if constexpr (TRAIN && !REC8) {
       if (lane == 0) {
         store_role(sm, 8, n_tiles, n_pairs, first, stride, tile_of,
                    [&](int item, int64_t tile) { return rec + tile * kRecBytes + kRecH0 + item * kHSBytes; },
@@ -337,7 +366,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     // this thread's (warp's) part of the next A operand is in smem; `record`: the tile is also a saved record
     auto a_ready_arrive = [&](int tl, bool record) {
       a_ready_arrive2(sm, tl, lane);
-      if (TRAIN && record) {
+      if (TRAIN && !REC8 && record) {   // (fp8 records leave from the epilogue's registers)
         st_ready_arrive(&sm.st_ready[tl], lane);
         st_pending |= 1u << tl;
       }
@@ -351,7 +380,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     };
     auto prologue = [&](int64_t pair, int tl, const float (&p)[3]) {
       const int64_t tile = tile_of(pair, tl);
-      pe_xyz(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRecBytes + kRecXS : nullptr, r, h, p[0], p[1], p[2]);
+      pe_xyz<REC8>(sm.xs[tl], (TRAIN && tile < n_tiles) ? rec + tile * kRB + kOffXS : nullptr, r, h, p[0], p[1], p[2]);
       a_ready_arrive(tl, false);
     };
 
@@ -373,7 +402,7 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
           const int64_t g = tile * kTileM + r;
           const bool valid = g < M;
           const bool save = TRAIN && tile < n_tiles;
-          uint8_t* rec_t = rec + tile * kRecBytes;
+          uint8_t* rec_t = rec + tile * kRB;
           KN_PROF_BEGIN(t_w);
           mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
           KN_PROF_END(t_w, 4);
@@ -393,11 +422,12 @@ tc_mlp_fwd_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                                                         __ldg(aux + 11 * 256 + 2));
             }
             hs_writable(tl);
-            epi_hidden<TRAIN>(tmem + lane_base + tl * 256, sm.hs[tl], h, r,
-                              save ? rec_t + kRecMask + s * kMaskLayerBytes : nullptr);
+            epi_hidden<TRAIN, REC8>(tmem + lane_base + tl * 256, sm.hs[tl], h, r,
+                                    save ? rec_t + kOffMask + s * kMaskLayerBytes : nullptr,
+                                    (REC8 && save) ? rec_t + kRec8H0 + s * kH8Bytes : nullptr);
             if (s == 5) {
               // xs[tl] is dead after layer 5 (skip concat consumed): it now carries PE(dir) for the last step
-              pe_dir(sm.xs[tl], save ? rec_t + kRecDS : nullptr, r, h, dirv[0], dirv[1], dirv[2]);
+              pe_dir<REC8>(sm.xs[tl], save ? rec_t + kOffDS : nullptr, r, h, dirv[0], dirv[1], dirv[2]);
               // Chunks 4..7 of xs[tl] are dead until the next tile's PE(xyz): they hold the fp32 weights of the
               // CUDA-core rgb head for the last step.  (With 227 KB of shared memory the SM has no L1: every __ldg
               // of them was an L2 round trip.)  Visibility to the other warps: every warp passes a_ready(5) ->
@@ -509,8 +539,8 @@ int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStrea
 }
 
 int tc_forward(const Model& m, const float* params, const void* packed, const float* o, const float* d, const float* t,
-               int64_t R, int S, bool training, bool ordered_issue, float* rgbsigma, char* ws, int64_t ws_bytes,
-               cudaStream_t st) {
+               int64_t R, int S, bool training, bool ordered_issue, bool rec8, float* rgbsigma, char* ws,
+               int64_t ws_bytes, cudaStream_t st) {
   (void)params;
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   const int64_t M = R * S;
@@ -538,12 +568,15 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   const uint8_t* pk = (const uint8_t*)packed;
   float4* out = (float4*)rgbsigma;
   uint8_t* rec = training ? (uint8_t*)ws + kXBytes : nullptr;
-  if (training) {
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
-    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<true>, pk, o, d, t, M, S, out, rec, ordered));
+  if (training && rec8) {
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<true, true>, pk, o, d, t, M, S, out, rec, ordered));
+  } else if (training) {
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<true, false>, pk, o, d, t, M, S, out, rec, ordered));
   } else {
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
-    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<false>, pk, o, d, t, M, S, out, rec, ordered));
+    KN_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_fwd_kernel<false, false>, pk, o, d, t, M, S, out, rec, ordered));
   }
   KN_LAUNCH_CHECK();
   return KNERF_OK;

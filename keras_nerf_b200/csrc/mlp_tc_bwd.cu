@@ -34,9 +34,11 @@ namespace {
 // (dst = record or nullptr) and must NOT touch hs[tl], which the other half-row thread of this row may already be
 // rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10) the dZ record.
 // mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
-template <int KIND>
+// REC8 (fp8 records): the dZ record leaves from here as e5m2(dZ * scale), 16 columns per 16-byte vector (rec8, nullptr
+// for a padding tile); dst is only the next A operand then (unused for KIND 3).
+template <int KIND, bool REC8>
 __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, uint4 mbv, float dsig,
-                                       const float* __restrict__ wsig) {
+                                       const float* __restrict__ wsig, uint8_t* __restrict__ rec8, float scale) {
   const uint32_t mb[4] = {mbv.x, mbv.y, mbv.z, mbv.w};   // by value: no local memory (no L1 on this SM)
 #pragma unroll
   for (int gI = 0; gI < 4; ++gI) {
@@ -49,6 +51,7 @@ __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst,
       for (int i = 0; i < 8; ++i) ws[i] = *(reinterpret_cast<const float4*>(wsig + col0) + i);   // shared memory
     }
     tmem_ld32_wait(v);
+    uint32_t q8[8];
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
       float x[8];
@@ -61,22 +64,46 @@ __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst,
       }
       uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                             pack_bf16x2(x[6], x[7]));
-      if (KIND >= 1) {
-        const uint32_t bits = mb[gI] >> (c8 * 4);
-        pk.x &= (bits & 0x00010001u) * 0xffffu;
-        pk.y &= ((bits >> 1) & 0x00010001u) * 0xffffu;
-        pk.z &= ((bits >> 2) & 0x00010001u) * 0xffffu;
-        pk.w &= ((bits >> 3) & 0x00010001u) * 0xffffu;
+      const uint32_t bits = mb[gI] >> (c8 * 4);
+      const uint32_t m0 = (bits & 0x00010001u) * 0xffffu, m1 = ((bits >> 1) & 0x00010001u) * 0xffffu,
+                     m2 = ((bits >> 2) & 0x00010001u) * 0xffffu, m3 = ((bits >> 3) & 0x00010001u) * 0xffffu;
+      pk.x &= m0; pk.y &= m1; pk.z &= m2; pk.w &= m3;
+      if (REC8) {   // byte masks of columns (0,1,2,3) / (4,5,6,7) from the half-word masks
+        q8[2 * c8] = pack_e5m2x4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale) & __byte_perm(m0, m1, 0x6420);
+        q8[2 * c8 + 1] = pack_e5m2x4(x[4] * scale, x[5] * scale, x[6] * scale, x[7] * scale) & __byte_perm(m2, m3, 0x6420);
+        if (KIND < 3) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
+      } else {
+        if (KIND < 3 || dst != nullptr) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
       }
-      if (KIND < 3 || dst != nullptr) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
+    }
+    if (REC8 && rec8 != nullptr) {
+      __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + 0) * kChunkA + r * 16), make_uint4(q8[0], q8[1], q8[2], q8[3]));
+      __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + 1) * kChunkA + r * 16), make_uint4(q8[4], q8[5], q8[6], q8[7]));
     }
   }
 }
 
+// fp8 records: max|d_pre| of the call (the bit pattern of a non-negative float orders like the float)
+__global__ void __launch_bounds__(256) dpre_amax_kernel(const float4* __restrict__ d_pre, int64_t M,
+                                                        uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(d_pre + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
 // clusters of 2, cta_group::2 MMAs (tc_roles2.cuh); a work unit is four tiles (two per CTA)
+template <bool REC8>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict__ d_pre, int64_t M,
-                    const uint8_t* __restrict__ rec, uint8_t* __restrict__ dz, float* __restrict__ grads, TcParams P) {
+                    const uint8_t* __restrict__ rec, uint8_t* __restrict__ dz, float* __restrict__ grads, TcParams P,
+                    float* __restrict__ xbuf) {
+  constexpr int kRB = REC8 ? kRec8Bytes : kRecBytes, kOffMask = REC8 ? kRec8Mask : kRecMask,
+                kDB = REC8 ? kDz8Bytes : kDzBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,7 +125,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     // record store: the A operands dZ7..dZ1 of the chain (items 1..7) are also the dZ records of the weight-gradient
     // kernel (tc_roles.cuh store_role); item 0 = dG only takes part in the hand-shake: nothing downstream reads it
     // from HBM (its weight gradients factor through d(rgb_pre), see build_task_table)
-    if (lane == 0) {
+    if (!REC8 && lane == 0) {   // (fp8 records leave from the epilogue's registers)
       store_role(sm, 8, n_tiles, n_pairs, first, stride, tile_of,
                  [&](int item, int64_t tile) {
                    return dz + tile * kDzBytes + (item == 0 ? kDzG : kDzZ0 + (8 - item) * kHSBytes);
@@ -109,8 +136,10 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     uint32_t st_pending = 0, st_par = 0;      // bit tl = hs[tl] is being stored / parity of st_done[tl]
     auto a_ready_arrive = [&](int tl) {   // this thread's (warp's) part of the next A operand (= dZ record) is in smem
       a_ready_arrive2(sm, tl, lane);
-      st_ready_arrive(&sm.st_ready[tl], lane);
-      st_pending |= 1u << tl;
+      if (!REC8) {
+        st_ready_arrive(&sm.st_ready[tl], lane);
+        st_pending |= 1u << tl;
+      }
     };
     auto hs_writable = [&](int tl) {          // the bulk store of the previous contents of hs[tl] has read them
       if ((st_pending >> tl) & 1) {
@@ -134,6 +163,8 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
     const float* wrgb = head + 256;
     uint32_t acc_par[2] = {0, 0};
     float dsig_keep0 = 0.f, dsig_keep1 = 0.f;
+    // fp8 records: one power-of-two scale per call, from max|d_pre| (written by dpre_amax_kernel before this launch)
+    const float scale = REC8 ? dz8_scale(__ldg(reinterpret_cast<const uint32_t*>(xbuf) + kXOffAmax), false) : 1.f;
 
     // tile start: dG = d(rgb_pre) Wc^T (K = 3, CUDA cores) becomes the first A operand
     auto prologue = [&](int64_t pair, int tl) {
@@ -143,17 +174,23 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < M) dp = d_pre[g];
       if (tl == 0) dsig_keep0 = dp.w; else dsig_keep1 = dp.w;
-      uint8_t* dz_t = dz + tile * kDzBytes;
-      if (active) {
+      uint8_t* dz_t = dz + tile * kDB;
+      if (active && !REC8) {
         const uint4 pk = (h == 0) ? make_uint4(pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u)
                                   : make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(dz_t + kDzP + h * kChunkA + r * 16) = pk;
       }
+      if (active && REC8 && h == 0)   // one 16-column chunk: (d rgb_pre, d sigma_pre) * scale, then zeros
+        *reinterpret_cast<uint4*>(dz_t + kDz8P + r * 16) =
+            make_uint4(pack_e5m2x4(dp.x * scale, dp.y * scale, dp.z * scale, dp.w * scale), 0u, 0u, 0u);
       if (h == 0) {   // bias gradients of the two heads: db_rgb = sum d(rgb_pre), db_sigma = sum d(sigma_pre)
         const float s0 = warp_sum(dp.x), s1 = warp_sum(dp.y), s2 = warp_sum(dp.z), s3 = warp_sum(dp.w);
         if (lane == 0) {
           atomicAdd(grads + P.b_off[11], s0); atomicAdd(grads + P.b_off[11] + 1, s1);
           atomicAdd(grads + P.b_off[11] + 2, s2); atomicAdd(grads + P.b_off[8], s3);
+          if (REC8) {   // sum d(rgb_pre) of THIS call for tc_finish_kernel (the bf16 path sums its operand copy instead)
+            atomicAdd(xbuf + kXOffS, s0); atomicAdd(xbuf + kXOffS + 1, s1); atomicAdd(xbuf + kXOffS + 2, s2);
+          }
         }
       }
       hs_writable(tl);
@@ -191,8 +228,8 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
         for (int tl = 0; tl < 2; ++tl) {
           const int64_t tile = tile_of(pair, tl);
           const bool active = tile < n_tiles;
-          uint8_t* out = dz + tile * kDzBytes + kDzZ0 + zi * kHSBytes;
-          const uint8_t* mask = rec + tile * kRecBytes + kRecMask + zi * kMaskLayerBytes;
+          uint8_t* out = REC8 ? dz + tile * kDB + kDz8Z0 + zi * kH8Bytes : dz + tile * kDB + kDzZ0 + zi * kHSBytes;
+          const uint8_t* mask = rec + tile * kRB + kOffMask + zi * kMaskLayerBytes;
           const float dsig = tl == 0 ? dsig_keep0 : dsig_keep1;
           // the ReLU' bits (written by the forward, 1 bit per activation) do not depend on the accumulator: fetch
           // this thread's 4 x 32 columns BEFORE waiting for the MMA so that the latency overlaps it
@@ -209,9 +246,10 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           // would run on every step)
           const uint32_t tacc = tmem + lane_base + tl * 256;
           const uint4 mbv = make_uint4(mb[0], mb[1], mb[2], mb[3]);
-          if (b == 0) epi_dgrad<1>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig);
-          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr);
-          else epi_dgrad<3>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr);
+          uint8_t* out8 = (REC8 && active) ? out : nullptr;
+          if (b == 0) epi_dgrad<1, REC8>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig, out8, scale);
+          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2, REC8>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr, out8, scale);
+          else epi_dgrad<3, REC8>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr, out8, scale);
           if (b + 1 < BwdProg::kSteps) {
             a_ready_arrive(tl);
           } else {
@@ -238,6 +276,11 @@ constexpr int kNumTasks = 10;
 // which holds its issuing thread as long as a wide one: measured 2.08 / 1.76 / 1.65 / 1.65 / 1.63 ns per sample for
 // the whole kernel at 50 / 80 / 110 / 140 / 178; 178 gives 217 + 36 + 43 = 296 items = exactly two per CTA.
 constexpr int kHeadsCost = 178;
+// fp8 records (build_task_table8): 64 KB and 16 MMAs per tile for a `big` task (cost 128), 40 KB / 8 MMAs for the two
+// encoding tasks, 38 KB / 12 narrow MMAs for the heads; 33 slabs -> 231 + 2 x 20 + 25 = 296 items = two per CTA
+constexpr int kXpartCost8 = 80;
+constexpr int kHeadsCost8 = 100;
+constexpr int kSlabs8 = 33;
 constexpr int kWMaxUnits = 6;
 
 // one ring slot: `bytes` from the forward (src 0) or dz (src 1) record at offset 0 and, optionally, `bytes2` from the
@@ -326,6 +369,62 @@ static WTaskTable build_task_table(int dx, int dd) {
   return T;
 }
 
+// fp8 records: a unit is a WHOLE 32 KB record (256 features x 128 samples); the 128 x 128 accumulator groups address
+// its halves through a_sub / b_sub.  64 KB per tile and `big` task instead of 128.
+static WTaskTable build_task_table8(int dx, int dd) {
+  WTaskTable T{};
+  int n = 0;
+  constexpr int kHalf = kH8Bytes / 2;
+  auto big = [&](int layer, int a_off, int b_off, int row_base) {
+    WTask& t = T.t[n++];
+    t.n_units = 2;
+    t.u[0] = {0, a_off, kH8Bytes, -1, 0, 0, 0}; t.u[1] = {1, b_off, kH8Bytes, layer, 0, 0, 0};
+    t.n_groups = 4;
+    t.g[0] = {0, 1, 0, 128, layer, row_base, 128, 0, 0, 0, 0, 0, 0};
+    t.g[1] = {0, 1, 128, 128, layer, row_base, 128, 128, 0, 0, 0, 0, kHalf};
+    t.g[2] = {0, 1, 256, 128, layer, row_base + 128, 128, 0, 0, 0, 0, kHalf, 0};
+    t.g[3] = {0, 1, 384, 128, layer, row_base + 128, 128, 128, 0, 0, 0, kHalf, kHalf};
+    t.cost = 128;
+  };
+  auto xpart = [&](int layer, int b_off, int row_base) {
+    WTask& t = T.t[n++];
+    t.n_units = 2;
+    const int bl = (layer == 0) ? 0 : -1;
+    t.u[0] = {0, kRec8XS, 8192, -1, 0, 0, 0}; t.u[1] = {1, b_off, kH8Bytes, bl, 0, 0, 0};
+    t.n_groups = 2;
+    t.g[0] = {0, 1, 0, 128, layer, row_base, dx, 0, 0, 0, 0, 0, 0};
+    t.g[1] = {0, 1, 128, 128, layer, row_base, dx, 128, 0, 0, 0, 0, kHalf};
+    t.cost = kXpartCost8;
+  };
+  xpart(0, kDz8Z0, 0);
+  for (int l = 1; l <= 7; ++l) big(l, kRec8H0 + (l - 1) * kH8Bytes, kDz8Z0 + l * kH8Bytes, 0);
+  xpart(5, kDz8Z0 + 5 * kH8Bytes, 256);
+  {
+    WTask& t = T.t[n++];
+    t.n_units = 2;
+    t.u[0] = {0, kRec8H0 + 7 * kH8Bytes, kH8Bytes, -1, 0, 0, 0};   // h7
+    t.u[1] = {0, kRec8DS, 4096, -1, 0, kDz8P, 2048};               // PE(dir) and, at +4096, the packed d_pre operand
+    t.n_groups = 3;
+    t.g[0] = {0, 1, 0, 16, 8, 0, 128, 0, 1, 0, 0, 0, 4096};
+    t.g[1] = {0, 1, 32, 16, 8, 128, 128, 0, 1, 0, 0, kHalf, 4096};
+    t.g[2] = {1, 1, 64, 16, -1, 0, dd, 0, 4, 0, 0, 0, 4096};
+    t.g[0].issuer = 0; t.g[1].issuer = 1; t.g[2].issuer = 0;
+    t.cost = kHeadsCost8;
+  }
+  for (int k = 0; k < n; ++k) {
+    WTask& t = T.t[k];
+    if (k != n - 1)
+      for (int gi = 0; gi < t.n_groups; ++gi) t.g[gi].issuer = gi & 1;
+    for (int x = 0; x < 2; ++x)
+      for (int u = 0; u < kWMaxUnits; ++u) {
+        t.last_grp[x][u] = -1;
+        for (int gi = 0; gi < t.n_groups; ++gi)
+          if (t.g[gi].issuer == x && (t.g[gi].a == u || t.g[gi].b == u)) t.last_grp[x][u] = (int8_t)gi;
+      }
+  }
+  return T;
+}
+
 struct WSmem {
   uint8_t slot[kWSlots][kWUnitBytes];
   uint64_t full[kWSlots], empty[kWSlots], acc_done, acc_free;
@@ -358,10 +457,13 @@ static int count_items(const WTaskTable& T, int slabs_per_cost_x128) {
   return n;
 }
 
+template <bool REC8>
 __global__ void __launch_bounds__(kWThreads, 1)
 tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz, int64_t n_tiles,
                 float* __restrict__ grads, float* __restrict__ xbuf, TcParams P, const __grid_constant__ WTaskTable T,
                 int n_items, int slabs) {
+  constexpr int kRB = REC8 ? kRec8Bytes : kRecBytes, kDB = REC8 ? kDz8Bytes : kDzBytes;
+  constexpr int kSub2 = REC8 ? 4096 : 8192;   // slot offset of a unit's second part (the packed d_pre operand)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -388,12 +490,12 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
         for (int64_t tile = w.tile_lo; tile < w.tile_hi; ++tile) {
           for (int k = 0; k < t.n_units; ++k, ++it) {
             const uint32_t slot = it % kWSlots, ph = (it / kWSlots) & 1;
-            const uint8_t* src = (t.u[k].src == 0 ? rec + tile * kRecBytes : dz + tile * kDzBytes) + t.u[k].off;
+            const uint8_t* src = (t.u[k].src == 0 ? rec + tile * kRB : dz + tile * kDB) + t.u[k].off;
             mbar_wait(&sm.empty[slot], ph ^ 1);
             mbar_arrive_expect_tx(&sm.full[slot], t.u[k].bytes + t.u[k].bytes2);
             tma_load_1d(sm.slot[slot], src, t.u[k].bytes, &sm.full[slot]);
             if (t.u[k].bytes2)
-              tma_load_1d(sm.slot[slot] + 8192, dz + tile * kDzBytes + t.u[k].off2, t.u[k].bytes2, &sm.full[slot]);
+              tma_load_1d(sm.slot[slot] + kSub2, dz + tile * kDB + t.u[k].off2, t.u[k].bytes2, &sm.full[slot]);
           }
         }
       }
@@ -422,13 +524,23 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             mbar_wait(&sm.full[sa], (ia / kWSlots) & 1);
             mbar_wait(&sm.full[sb], (ib / kWSlots) & 1);
             tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16(128, g.N, 1, 1);
             const uint32_t a_base = smem_u32(sm.slot[sa]) + g.a_sub, b_base = smem_u32(sm.slot[sb]) + g.b_sub;
+            if (REC8) {   // e4m3 activations x e5m2 gradients, 32 samples per MMA (512 B further along every chunk)
+              const uint32_t idesc = umma_idesc_f8(128, g.N, kE4M3, kE5M2, 1, 1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // K = 128 samples per tile, 16 per MMA; MN-major: LBO = 128 B, SBO = 2 KB
-              const uint64_t da = umma_smem_desc(a_base + k * 256, 128, kChunkA);
-              const uint64_t db = umma_smem_desc(b_base + k * 256, 128, kChunkA);
-              umma_bf16(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_smem_desc(a_base + k * 512, 128, kChunkA);
+                const uint64_t db = umma_smem_desc(b_base + k * 512, 128, kChunkA);
+                umma_f8(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
+              }
+            } else {
+              const uint32_t idesc = umma_idesc_bf16(128, g.N, 1, 1);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {   // K = 128 samples per tile, 16 per MMA; MN-major: LBO = 128 B, SBO = 2 KB
+                const uint64_t da = umma_smem_desc(a_base + k * 256, 128, kChunkA);
+                const uint64_t db = umma_smem_desc(b_base + k * 256, 128, kChunkA);
+                umma_bf16(tmem + g.col, da, db, idesc, (tile > w.tile_lo || k > 0) ? 1u : 0u);
+              }
             }
             if (t.last_grp[me][g.a] == gi) umma_commit(&sm.empty[sa]);
             if (g.b != g.a && t.last_grp[me][g.b] == gi) umma_commit(&sm.empty[sb]);
@@ -458,6 +570,8 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
       // While the tensor core works through the item, these warps take the bias gradients: column sums (over
       // samples) of every dZ unit passing through shared memory.  Thread (fc, fsub) owns 8 columns of chunk fc
       // and every 8th sample; partial sums stay in registers for the whole item.
+      // (fp8 records: a task has ONE dZ unit of 16 chunks x 16 columns; bacc[0] / bacc[1] = columns 0..7 / 8..15 of chunk fc)
+      const float inv_scale = REC8 ? dz8_scale(__ldg(reinterpret_cast<const uint32_t*>(xbuf) + kXOffAmax), true) : 1.f;
       float bacc[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u)
@@ -471,16 +585,30 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
           mbar_wait(&sm.full[slot], (uit / kWSlots) & 1);
           if (t.u[k].bias_layer >= 0) {
             const uint8_t* base = sm.slot[slot] + fc * kChunkA + fsub * 16;
-            float* a = bacc[nb & 1];
+            if (REC8) {
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-              const uint4 v = *reinterpret_cast<const uint4*>(base + i * 128);
-              a[0] += bf16_lo(v.x); a[1] += bf16_hi(v.x); a[2] += bf16_lo(v.y); a[3] += bf16_hi(v.y);
-              a[4] += bf16_lo(v.z); a[5] += bf16_hi(v.z); a[6] += bf16_lo(v.w); a[7] += bf16_hi(v.w);
+              for (int i = 0; i < 16; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(base + i * 128);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 lo = e5m2x2_lo(wv[j]), hi = e5m2x2_hi(wv[j]);
+                  float* a = bacc[j >> 1] + (j & 1) * 4;
+                  a[0] += lo.x; a[1] += lo.y; a[2] += hi.x; a[3] += hi.y;
+                }
+              }
+            } else {
+              float* a = bacc[nb & 1];
+#pragma unroll 4
+              for (int i = 0; i < 16; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(base + i * 128);
+                a[0] += bf16_lo(v.x); a[1] += bf16_hi(v.x); a[2] += bf16_lo(v.y); a[3] += bf16_hi(v.y);
+                a[4] += bf16_lo(v.z); a[5] += bf16_hi(v.z); a[6] += bf16_lo(v.w); a[7] += bf16_hi(v.w);
+              }
             }
             ++nb;
           }
-          if (t.u[k].bytes2 != 0) {   // the d_pre operand at +8192: [2 chunks][128 rows][8], chunk 0 = (r, g, b, sigma, 0..)
+          if (!REC8 && t.u[k].bytes2 != 0) {   // the d_pre operand at +8192: [2 chunks][128 rows][8], chunk 0 = (r, g, b, sigma, 0..)
             const uint2 v = *reinterpret_cast<const uint2*>(sm.slot[slot] + 8192 + ftid * 16);   // one row per thread: this
             pacc[0] += bf16_lo(v.x); pacc[1] += bf16_hi(v.x); pacc[2] += bf16_lo(v.y);           // sits on the slot-release path
           }
@@ -492,22 +620,26 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
         int nb = 0;
         for (int k = 0; k < t.n_units; ++k) {
           if (t.u[k].bias_layer < 0) continue;
-          float* a = bacc[nb & 1];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 1);
-            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 2);
-            a[e] += __shfl_xor_sync(0xffffffffu, a[e], 4);
-          }
-          if (fsub == 0) {
-            float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + fc * 8;
+          for (int u = 0; u < 2; ++u) {
+            if (!REC8 && u != (nb & 1)) continue;
+            float* a = bacc[u];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e]);
+            for (int e = 0; e < 8; ++e) {
+              a[e] += __shfl_xor_sync(0xffffffffu, a[e], 1);
+              a[e] += __shfl_xor_sync(0xffffffffu, a[e], 2);
+              a[e] += __shfl_xor_sync(0xffffffffu, a[e], 4);
+            }
+            if (fsub == 0) {
+              float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + (REC8 ? fc * 16 + u * 8 : fc * 8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e] * inv_scale);
+            }
           }
           ++nb;
         }
       }
-      if (w.task == kNumTasks - 1) {   // heads task: sum d(rgb_pre) of this call for tc_finish_kernel
+      if (!REC8 && w.task == kNumTasks - 1) {   // heads task: sum d(rgb_pre) of this call for tc_finish_kernel
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
           const float sres = warp_sum(pacc[e]);
@@ -523,6 +655,10 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
         for (int c0 = 0; c0 < ncol; c0 += 32) {
           float v[32];
           tmem_ld32(tmem + lane_base + g.col + c0, v);   // warp-collective: outside the row guard
+          if (REC8) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= inv_scale;
+          }
           if (row < g.row_limit) {
             if (g.mode == 0) {
               const int ld = (g.layer == 10) ? 128 : 256;
@@ -639,7 +775,7 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
 
 // parts: which of the backward kernels to launch (bit 0 dgrad, bit 1 wgrad + finish; KNERF_BWD_*_ONLY)
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
-                float* grads, char* ws, int64_t ws_bytes, int parts, cudaStream_t st) {
+                float* grads, char* ws, int64_t ws_bytes, int parts, bool rec8, cudaStream_t st) {
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
@@ -650,8 +786,12 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   const int64_t n_tiles = cdiv(M, kTileM);
   float* xbuf = (float*)ws;                                // X = h7^T dG and sum(dG) of this call
   uint8_t* rec = (uint8_t*)ws + kXBytes;
-  uint8_t* dz = rec + n_tiles * (int64_t)kRecBytes;
+  uint8_t* dz = rec + n_tiles * (int64_t)(rec8 ? kRec8Bytes : kRecBytes);
   const TcParams P = tc_make_params(m);
+  // the fp32 scratch (rank-3 factors, sum d(rgb_pre), max|d_pre|) starts from zero in every call -- except that a
+  // weight-gradient-only call (KNERF_BWD_WGRAD_ONLY) over fp8 records keeps what the dgrad-only call before it left
+  // there: sum d(rgb_pre) and the scale of the gradient records
+  KN_CUDA(cudaMemsetAsync(xbuf, 0, ((rec8 && parts == 2) ? kXOffS : kXFloats) * sizeof(float), st));
 
   if (parts & 1) {
     cudaLaunchConfig_t cfg{};
@@ -667,20 +807,32 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
     const uint8_t* pk = (const uint8_t*)packed;
     const float4* dp = (const float4*)d_pre;
     const uint8_t* rec_c = rec;
-    KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
-    KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel, pk, dp, M, rec_c, dz, grads, P));
+    if (rec8) {
+      dpre_amax_kernel<<<kNumSMs * 4, 256, 0, st>>>(dp, M, reinterpret_cast<uint32_t*>(xbuf) + kXOffAmax);
+      KN_LAUNCH_CHECK();
+      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<true>, pk, dp, M, rec_c, dz, grads, P, xbuf));
+    } else {
+      KN_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+      KN_CUDA(cudaLaunchKernelEx(&cfg, tc_mlp_dgrad_kernel<false>, pk, dp, M, rec_c, dz, grads, P, xbuf));
+    }
     KN_LAUNCH_CHECK();
   }
   if (parts & 2) {
-    const WTaskTable h_table = build_task_table(m.dx, m.dd);   // ~3 KB, passed by value as a __grid_constant__
+    // ~3 KB, passed by value as a __grid_constant__
+    const WTaskTable h_table = rec8 ? build_task_table8(m.dx, m.dd) : build_task_table(m.dx, m.dd);
     // items = 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 178 -> 217 + 36 + 43 = 296 items for 31 slabs
-    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(31, n_tiles / 4));
+    const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(rec8 ? kSlabs8 : 31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);
     const int grid = std::min(n_items, kNumSMs);
     const size_t smem = sizeof(WSmem);
-    KN_CUDA(cudaMemsetAsync(xbuf, 0, kXFloats * sizeof(float), st));
-    KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
+    if (rec8) {
+      KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_wgrad_kernel<true><<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
+    } else {
+      KN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_wgrad_kernel<false><<<grid, kWThreads, smem, st>>>(rec, dz, n_tiles, grads, xbuf, P, h_table, n_items, slabs);
+    }
     KN_LAUNCH_CHECK();
     tc_finish_prep_kernel<<<6, 256, 0, st>>>(params, P, xbuf);
     KN_LAUNCH_CHECK();

@@ -53,8 +53,8 @@ static int mlp_forward_impl(const Model& m, const float* params, const void* pac
   }
   if (precision == KNERF_BF16) {
     if (packed == nullptr) return fail(KNERF_ERR_INVALID, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
-    return tc_forward(m, params, packed, o, d, t, R, S, training, (precision_flags & KNERF_TC_ORDERED) != 0, rgbsigma,
-                      ws, ws_bytes, st);
+    return tc_forward(m, params, packed, o, d, t, R, S, training, (precision_flags & KNERF_TC_ORDERED) != 0,
+                      (precision_flags & KNERF_REC_FP8) != 0, rgbsigma, ws, ws_bytes, st);
   }
   return fail(KNERF_ERR_INVALID, "unknown precision %d", precision);
 }
@@ -73,7 +73,8 @@ static int mlp_backward_impl(const Model& m, const float* params, const void* pa
   }
   if (precision == KNERF_BF16) {
     const int parts = (precision_flags & KNERF_BWD_DGRAD_ONLY) ? 1 : (precision_flags & KNERF_BWD_WGRAD_ONLY) ? 2 : 3;
-    return tc_backward(m, params, packed, d_pre, R, S, grads, ws, ws_bytes, parts, st);
+    return tc_backward(m, params, packed, d_pre, R, S, grads, ws, ws_bytes, parts, (precision_flags & KNERF_REC_FP8) != 0,
+                       st);
   }
   return fail(KNERF_ERR_INVALID, "unknown precision %d", precision);
 }

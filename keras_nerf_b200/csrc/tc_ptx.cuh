@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace knerf {
@@ -186,6 +187,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// kind::f8f6f4, fp8 x fp8 -> fp32 (K = 32 per instruction): same descriptor fields, a_format / b_format 0 = E4M3,
+// 1 = E5M2 (cute::UMMA::InstrDescriptor).  8-bit operands may be MN-major too; the chunk-major layout becomes
+// [rows/16 chunks][K][16 elements] -- still one 16-byte vector per (chunk, k), LBO = 128 B (next 8 k), SBO = K * 16 B.
+constexpr int kE4M3 = 0, kE5M2 = 1;
+__host__ __device__ constexpr uint32_t umma_idesc_f8(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -209,6 +227,43 @@ __device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t p) {
   uint32_t m;
   asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(p), "r"(0u));
   return m;
+}
+// four fp32 -> four fp8 bytes (byte i = value i), round to nearest, saturating to the largest finite value
+__device__ __forceinline__ uint32_t pack_e4m3x4_relu(float a, float b, float c, float d) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.relu.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.relu.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e5m2x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e5m2x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r) : "f"(a), "f"(b), "f"(c), "f"(d));
+  return r;
+}
+// an e5m2 byte is the upper byte of the fp16 with the same value: bytes (0, 1) / (2, 3) of a word -> two fp32
+__device__ __forceinline__ float2 e5m2x2_lo(uint32_t w) {
+  const uint32_t h = __byte_perm(w, 0u, 0x1404);
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ float2 e5m2x2_hi(uint32_t w) {
+  const uint32_t h = __byte_perm(w, 0u, 0x3424);
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }

@@ -10,6 +10,8 @@ using namespace tc;
 
 // mode 0: A blob [K/8][128][8], B blob [K/8][N][8]           (K-major, K = reduction)
 // mode 1: A blob [128/8][K][8], B blob [N/8][K][8]           (MN-major, K = rows of the blobs)
+// mode 2: A blob [128/16][K][16] e4m3, B blob [N/16][K][16] e5m2   (MN-major fp8, kind::f8f6f4: the weight-gradient
+//         GEMM over fp8 records)
 __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const uint8_t* __restrict__ a_blob,
                                                             const uint8_t* __restrict__ b_blob, int N, int K,
                                                             float* __restrict__ d_out) {
@@ -17,7 +19,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const uint
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_bytes = 128u * K * 2u, b_bytes = (uint32_t)N * K * 2u;
+  const uint32_t esz = mode == 2 ? 1u : 2u;
+  const uint32_t a_bytes = 128u * K * esz, b_bytes = (uint32_t)N * K * esz;
   uint8_t* sa = smem;
   uint8_t* sb = smem + a_bytes;
   if (tid == 0) {
@@ -36,8 +39,16 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const uint
     tma_load_1d(sb, b_blob, b_bytes, &bar_load);
     mbar_wait(&bar_load, 0);
     tc_fence_after();
+    if (mode == 2) {
+      const uint32_t idesc8 = umma_idesc_f8(128, N, kE4M3, kE5M2, 1, 1);
+      for (int k = 0; k < K / 32; ++k) {   // 32 k per instruction = 32 rows x 16 B of every chunk
+        const uint64_t da = umma_smem_desc(smem_u32(sa) + k * 512, 128, K * 16);
+        const uint64_t db = umma_smem_desc(smem_u32(sb) + k * 512, 128, K * 16);
+        umma_f8(tmem, da, db, idesc8, k > 0 ? 1u : 0u);
+      }
+    }
     const uint32_t idesc = umma_idesc_bf16(128, N, mode, mode);
-    for (int k = 0; k < K / 16; ++k) {
+    for (int k = 0; k < (mode == 2 ? 0 : K / 16); ++k) {
       uint64_t da, db;
       if (mode == 0) {
         da = umma_smem_desc(smem_u32(sa) + k * 2 * (128 * 16), 128 * 16, 128);
@@ -57,7 +68,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, const uint
     float v[32];
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) d_out[(size_t)row * N + c0 + i] = v[i];
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < N) d_out[(size_t)row * N + c0 + i] = v[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -138,9 +150,14 @@ extern "C" int knerf_selftest_umma2(const void* a_blob, const void* b_blob, int 
 extern "C" int knerf_selftest_umma(int mode, const void* a_blob, const void* b_blob, int N, int K, float* d_out,
                                    void* stream) {
   KN_CHECK_ARG(a_blob && b_blob && d_out, "knerf_selftest_umma: null pointer");
-  KN_CHECK_ARG((mode == 0 || mode == 1) && N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256,
-               "knerf_selftest_umma: mode 0/1, N in 32..256 step 32, K in 16..256 step 16");
-  const size_t smem = (size_t)(128 + N) * K * 2;
+  if (mode == 2) {
+    KN_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 32 == 0 && K >= 32 && K <= 256,
+                 "knerf_selftest_umma: mode 2, N in 16..256 step 16, K in 32..256 step 32");
+  } else {
+    KN_CHECK_ARG((mode == 0 || mode == 1) && N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256,
+                 "knerf_selftest_umma: mode 0/1, N in 32..256 step 32, K in 16..256 step 16");
+  }
+  const size_t smem = (size_t)(128 + N) * K * (mode == 2 ? 1 : 2);
   KN_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, (const uint8_t*)a_blob, (const uint8_t*)b_blob, N,
                                                                K, d_out);

@@ -109,7 +109,7 @@ class NeRF:
     def __init__(self, n_coarse: int = 64, n_fine: int = 128, pos_emb_xyz: int = 10, pos_emb_dir: int = 4,
                  n_layers: int = 8, dense_units: int = 256, skip_layer=4, model_path: str = None,
                  precision: str = "fp32", oob_mode: str = "zero", scan_mode: str = None, device=None,
-                 strategy=None, reproducible: bool = False, **kwargs):
+                 strategy=None, reproducible: bool = False, records: str = "bf16", **kwargs):
         # keras_nerf/model/nerf/nerf.py:11-43
         self.model_path = model_path
         if self.model_path is None:
@@ -135,6 +135,10 @@ class NeRF:
         # pixels); reproducible=True makes them hand over in order like the training kernels (-14 % throughput).
         # A per-call option of the library (KNERF_TC_ORDERED), i.e. per model: other models are unaffected.
         self.reproducible = bool(reproducible)
+        # bf16 training: storage format of the records saved for the weight-gradient GEMMs (KNERF_REC_FP8)
+        if records not in ("bf16", "fp8"):
+            raise ValueError("records must be 'bf16' or 'fp8'")
+        self.records = records
         self.coarse = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
                               name='coarse_nerf', device=device)
         self.fine = NeRFMLP(n_layers=self.n_layers, dense_units=self.dense_units, skip_layer=self.skip_layer,
@@ -230,6 +234,9 @@ class NeRF:
                                 lib.knerf_last_error().decode() or "unsupported configuration")
                 self.precision, self._prec = "fp32_tc", _lib.FP32_TC
         self._prec_flags = self._prec | (_lib.TC_ORDERED if self.reproducible else 0)
+        if self._prec == _lib.BF16 and self.records == "fp8":
+            self._prec_flags |= _lib.REC_FP8
+        self._prec_train = self._prec | (self._prec_flags & _lib.REC_FP8)      # (tests drive the kernels one by one)
         if self._prec == _lib.BF16:
             for name in ("coarse", "fine"):
                 self._packed[name] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
