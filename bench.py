@@ -163,12 +163,15 @@ def run_reference(args, emit):
     emit(line)
 
 
-def workload_config(precision, ray_chunks):
+def workload_config(precision, ray_chunks, records=None):
     return {"workload": "BASELINE config[3]: coarse+fine NeRF train step, 32768 rays/GPU (128x256 crops of 400x400 "
                         "synthetic orbit views), 64 coarse + 128 fine samples, 8x256 MLPs, white bg, Adam, "
                         "ray-sharded DP",
             "rays_per_gpu": RAYS_PER_GPU, "image_wh": IMG_WH, "n_coarse": N_COARSE, "n_fine": N_FINE,
             "precision_mode": precision, "ray_chunks": ray_chunks,
+            # bf16 mode only: storage format of the activation / gradient records between the training kernels (forward
+            # outputs and the dgrad chain are the same bits with either; `--records bf16` runs round 1's format)
+            "records": records if precision == "bf16" else None,
             "l2": "per-step working set (activations of 6.3M samples) is >> 126 MB L2; inputs rotate over 4 batches"}
 
 
@@ -180,6 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp32_tc"])
+    ap.add_argument("--records", default="fp8", choices=["bf16", "fp8"], help="bf16 mode: format of the saved records")
     ap.add_argument("--ray-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the secondary 800x800 render metric")
@@ -222,7 +226,7 @@ def main():
     ray_chunks = args.ray_chunks or (RAYS_PER_GPU if precision == "bf16" else 4096)
 
     mlp_mod.set_seed(42)
-    model = NeRF(precision=precision, strategy=strategy, device=dev)
+    model = NeRF(precision=precision, strategy=strategy, device=dev, records=args.records)
     model.compile(optimizer="adam", loss="mse", batch_size=1, image_height=RAYS_PER_GPU // 256, image_width=256,
                   ray_chunks=ray_chunks, white_background=True)
     if strategy is not None:
@@ -336,7 +340,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(precision, ray_chunks),
+            "config": workload_config(precision, ray_chunks, args.records),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8 + 4 * 4, "ms_per_step": e2e_ms / args.steps,
                     "pipeline": "step i + 1's H2D copy on a copy stream while step i computes; one D2H read per step"},

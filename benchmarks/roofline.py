@@ -23,14 +23,20 @@ FLOP_DGRAD_PER_SAMPLE = FLOP_TRAIN_PER_SAMPLE - FLOP_FWD_PER_SAMPLE - FLOP_WGRAD
 BYTES_FWD_SAVE = 568 * 1024 / 128                       # forward writes the activation record (+ ReLU' bits) once
 BYTES_DGRAD = 8 * 32 + 516 * 1024 / 128                 # reads the 8 x 1-bit ReLU' tiles, writes dZ0..dZ7 + the d_pre operand
 BYTES_WGRAD = 1132 * 1024 / 128                         # operand units of the 10 weight-gradient tasks
+# the same with fp8 records (KNERF_REC_FP8, the default; tc_layout.cuh kRec8* / kDz8*)
+BYTES8_FWD_SAVE = 300 * 1024 / 128                      # PE(xyz) 8 + PE(dir) 4 + h0..h7 256 + ReLU' bits 32 KB per tile
+BYTES8_DGRAD = 8 * 32 + 16 + 258 * 1024 / 128           # reads the ReLU' tiles and d_pre, writes dZ0..dZ7 + the d_pre operand
+BYTES8_WGRAD = 566 * 1024 / 128                         # 2 x 40 + 7 x 64 + 38 KB per tile
 # measured DRAM traffic per sample (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture,
 # divided by the samples of that launch): profiles/ncu_traffic.json, written from the capture named inside it
-def _ncu_traffic():
+def _ncu_traffic(records="bf16"):
     import json
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return {}, None
     d = json.load(open(p))
+    if records == "fp8":
+        d = d.get("fp8_records", {})
     return d.get("dram_bytes_per_sample", {}), d.get("source")
 
 
@@ -62,7 +68,8 @@ def dominant_kernel_roofline(model, precision, peaks):
     rgbs = torch.empty(R, S, 4, device=dev)
     dpre = (torch.randn(R, S, 4, generator=g) * 1e-4).to(dev)
     grads = torch.zeros_like(model.fine.params)
-    prec = model._prec
+    prec = model._prec_train
+    rec8 = bool(prec & _lib.REC_FP8)
     packed = model._packed_ptr("fine")
     ws, wsn = model._ws.data_ptr(), model._ws.numel()
     lib = _lib.load()
@@ -82,7 +89,7 @@ def dominant_kernel_roofline(model, precision, peaks):
     # its kernels, which an ideal fused implementation would not move at all.
     bf16_peak, bf16_sus, hbm_peak = peaks["bf16_tflops"], peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
     src = f"{peaks['source']} (MEASURED_PEAKS.json: cuBLAS bf16 burst -- kernels timed alone --, copy bandwidth)"
-    traffic_ps, traffic_src = _ncu_traffic()
+    traffic_ps, traffic_src = _ncu_traffic("fp8" if rec8 else "bf16")
     kernels = {}
 
     def add(name, ms, flop_ps, bytes_ps, launches):
@@ -102,9 +109,11 @@ def dominant_kernel_roofline(model, precision, peaks):
     n_f = int(lib.knerf_launch_count() - l0)
     ms_f = _time_ms(fwd)
     if precision == "bf16":
-        add("tc_mlp_fwd_kernel<train>", ms_f, FLOP_FWD_PER_SAMPLE, BYTES_FWD_SAVE, n_f)
-        add("tc_mlp_dgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_DGRAD_ONLY)), FLOP_DGRAD_PER_SAMPLE, BYTES_DGRAD, 1)
-        add("tc_wgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_WGRAD_ONLY)), FLOP_WGRAD_PER_SAMPLE, BYTES_WGRAD, 2)
+        add("tc_mlp_fwd_kernel<train>", ms_f, FLOP_FWD_PER_SAMPLE, BYTES8_FWD_SAVE if rec8 else BYTES_FWD_SAVE, n_f)
+        add("tc_mlp_dgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_DGRAD_ONLY)), FLOP_DGRAD_PER_SAMPLE,
+            BYTES8_DGRAD if rec8 else BYTES_DGRAD, 2 if rec8 else 1)
+        add("tc_wgrad_kernel", _time_ms(lambda: bwd(_lib.BWD_WGRAD_ONLY)), FLOP_WGRAD_PER_SAMPLE,
+            BYTES8_WGRAD if rec8 else BYTES_WGRAD, 2)
     else:
         tag = ("fp32_tc forward (encode + tcx_pack + tcx_gemm_kernel + skinny heads)" if precision == "fp32_tc"
                else "fp32 forward (encode + sgemm_kernel + skinny heads)")
@@ -127,6 +136,9 @@ def dominant_kernel_roofline(model, precision, peaks):
                                if per_sample else None),
             "design_bytes_hbm_frac": k.get("design_bytes_hbm_frac"),
             "samples_per_launch": rows, "peak_source": src, "kernels": kernels}
+    if precision == "bf16":
+        roof["records"] = "fp8 (e4m3 activations / e5m2 gradients for the weight-gradient GEMMs)" if rec8 else "bf16"
+        roof["design_bytes_per_sample_step"] = sum(kernels[k].get("design_bytes_per_sample", 0) for k in kernels)
     if precision == "fp32_tc":
         roof["note"] = ("fp32-grade mode on the tensor cores: every product is six bf16 MMAs, so 1/6 of the bf16 peak "
                         "(270 TFLOP/s burst) is its ceiling; TFLOP/s count the fp32 work once")

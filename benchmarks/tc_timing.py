@@ -20,7 +20,8 @@ def main():
     from keras_nerf_b200.model.nerf import mlp as mlp_mod
     dev = torch.device("cuda", 0)
     mlp_mod.set_seed(42)
-    model = NeRF(precision="bf16", device=dev)
+    records = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    model = NeRF(precision="bf16", device=dev, records=records)
     model.compile(optimizer="adam", loss="mse", batch_size=1, image_height=R // 64, image_width=64, ray_chunks=R,
                   white_background=True)
     g = torch.Generator(device="cpu").manual_seed(0)
@@ -36,7 +37,7 @@ def main():
     for train in (0, 1):
         for it in range(3):
             _lib.call("knerf_mlp_forward", C.byref(model.cfg), _lib.ptr(model.fine.params), packed, _lib.ptr(o),
-                      _lib.ptr(d), _lib.ptr(t), R, S, model._prec, train, _lib.ptr(rgbs), ws, wsn, _lib.stream())
+                      _lib.ptr(d), _lib.ptr(t), R, S, model._prec_train, train, _lib.ptr(rgbs), ws, wsn, _lib.stream())
             torch.cuda.synchronize()
             n = lib.knerf_debug_tc_timing(buf, 160 * 40)
         if n == 0:

@@ -157,7 +157,8 @@ int64_t knerf_param_count(const knerf_config* cfg);
 int knerf_layer_table(const knerf_config* cfg, int max_layers, int64_t* kernel_off, int64_t* bias_off,
                       int32_t* fan_in, int32_t* fan_out);
 
-/* bytes of scratch the MLP / chunk entry points need for `rows` = R*S samples */
+/* bytes of scratch the MLP / chunk entry points need for `rows` = R*S samples (`precision` with the option bits
+ * the calls will carry: KNERF_REC_FP8 halves the training records) */
 int64_t knerf_workspace_bytes(const knerf_config* cfg, int64_t rows, int precision, int training);
 
 /* NeRFMLP.call on already-encoded inputs: xyz[rows, ld_xyz], dirs[rows, ld_dir] -> rgb[rows,3],

@@ -107,10 +107,11 @@ extern "C" int64_t knerf_workspace_bytes(const knerf_config* cfg, int64_t rows, 
   Model m;
   if (build_model(cfg, &m) != KNERF_OK || rows < 0) return -1;
   int64_t mlp = 0;
+  const bool rec8 = (precision & KNERF_REC_FP8) != 0;
   precision &= KNERF_PRECISION_MASK;
   if (precision == KNERF_FP32 || precision == KNERF_FP32_TC)
     mlp = (int64_t)make_fp32_plan(m, rows, training != 0, precision == KNERF_FP32_TC).total;
-  else if (precision == KNERF_BF16) mlp = tc_workspace_bytes(m, rows, training != 0);
+  else if (precision == KNERF_BF16) mlp = tc_workspace_bytes(m, rows, training != 0, rec8);
   else return -1;
   if (mlp < 0) return -1;
   // chunk-level scratch of knerf_render_chunk / knerf_train_chunk: rgbsigma + d_pre (16 B/row each),

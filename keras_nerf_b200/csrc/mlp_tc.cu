@@ -514,10 +514,10 @@ int tc_debug_timing(unsigned long long* host_out, int n) {
 
 int64_t tc_packed_weight_bytes(const Model& m) { return is_flagship(m) ? kPackedBytes : -1; }
 
-int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training) {
+int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training, bool rec8) {
   if (!is_flagship(m)) return -1;
   if (!training) return 256;
-  return kXBytes + cdiv(rows, kTileM) * (int64_t)(kRecBytes + kDzBytes) + 256;
+  return kXBytes + cdiv(rows, kTileM) * (int64_t)(rec8 ? kRec8Bytes + kDz8Bytes : kRecBytes + kDzBytes) + 256;
 }
 
 TcParams tc_make_params(const Model& m) {
@@ -544,9 +544,9 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
   (void)params;
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   const int64_t M = R * S;
-  if (training && ws_bytes < tc_workspace_bytes(m, M, true))
+  if (training && ws_bytes < tc_workspace_bytes(m, M, true, rec8))
     return fail(KNERF_ERR_WORKSPACE, "tc_forward: workspace %lld < %lld bytes", (long long)ws_bytes,
-                (long long)tc_workspace_bytes(m, M, true));
+                (long long)tc_workspace_bytes(m, M, true, rec8));
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(rgbsigma) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
                "tc_forward: rgbsigma / packed / workspace must be 16-byte aligned");

@@ -5,7 +5,7 @@
 namespace knerf {
 
 bool tc_path_compiled();
-int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training);   // -1: shape unsupported
+int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training, bool rec8 = false);   // -1: shape unsupported
 int64_t tc_packed_weight_bytes(const Model& m);
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st);
 // (o,d,t) -> rgbsigma[R*S,4]; training keeps activations in ws.  ordered: the two MMA-issuing threads hand over in

@@ -278,9 +278,14 @@ constexpr int kNumTasks = 10;
 constexpr int kHeadsCost = 178;
 // fp8 records (build_task_table8): 64 KB and 16 MMAs per tile for a `big` task (cost 128), 40 KB / 8 MMAs for the two
 // encoding tasks, 38 KB / 12 narrow MMAs for the heads; 33 slabs -> 231 + 2 x 20 + 25 = 296 items = two per CTA
-constexpr int kXpartCost8 = 80;
-constexpr int kHeadsCost8 = 100;
-constexpr int kSlabs8 = 33;
+#ifndef KNERF_WG8_X   // (scratch builds for the balance measurements pass the three numbers as macros)
+#define KNERF_WG8_X 80
+#define KNERF_WG8_H 100
+#define KNERF_WG8_S 33
+#endif
+constexpr int kXpartCost8 = KNERF_WG8_X;
+constexpr int kHeadsCost8 = KNERF_WG8_H;
+constexpr int kSlabs8 = KNERF_WG8_S;
 constexpr int kWMaxUnits = 6;
 
 // one ring slot: `bytes` from the forward (src 0) or dz (src 1) record at offset 0 and, optionally, `bytes2` from the
@@ -779,9 +784,9 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
-  if (ws_bytes < tc_workspace_bytes(m, M, true))
+  if (ws_bytes < tc_workspace_bytes(m, M, true, rec8))
     return fail(KNERF_ERR_WORKSPACE, "tc_backward: workspace %lld < %lld bytes", (long long)ws_bytes,
-                (long long)tc_workspace_bytes(m, M, true));
+                (long long)tc_workspace_bytes(m, M, true, rec8));
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_pre) & 15) == 0, "tc_backward: d_pre must be 16-byte aligned");
   const int64_t n_tiles = cdiv(M, kTileM);
   float* xbuf = (float*)ws;                                // X = h7^T dG and sum(dG) of this call

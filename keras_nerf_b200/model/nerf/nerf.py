@@ -109,7 +109,7 @@ class NeRF:
     def __init__(self, n_coarse: int = 64, n_fine: int = 128, pos_emb_xyz: int = 10, pos_emb_dir: int = 4,
                  n_layers: int = 8, dense_units: int = 256, skip_layer=4, model_path: str = None,
                  precision: str = "fp32", oob_mode: str = "zero", scan_mode: str = None, device=None,
-                 strategy=None, reproducible: bool = False, records: str = "bf16", **kwargs):
+                 strategy=None, reproducible: bool = False, records: str = "fp8", **kwargs):
         # keras_nerf/model/nerf/nerf.py:11-43
         self.model_path = model_path
         if self.model_path is None:
@@ -135,7 +135,11 @@ class NeRF:
         # pixels); reproducible=True makes them hand over in order like the training kernels (-14 % throughput).
         # A per-call option of the library (KNERF_TC_ORDERED), i.e. per model: other models are unaffected.
         self.reproducible = bool(reproducible)
-        # bf16 training: storage format of the records saved for the weight-gradient GEMMs (KNERF_REC_FP8)
+        # bf16 training: storage format of the records the forward / dgrad kernels save for the weight-gradient GEMMs.
+        # "fp8" (KNERF_REC_FP8: e4m3 activations, e5m2 gradients under one power-of-two scale per call) halves the
+        # step's HBM traffic; forward outputs and the dgrad chain are the same bits either way, the weight gradients
+        # differ by 0.3-0.7 % (relative L2 at 98k samples) and training converges alike (profiles/r02_fp8_records.md).
+        # "bf16" keeps round 1's records.
         if records not in ("bf16", "fp8"):
             raise ValueError("records must be 'bf16' or 'fp8'")
         self.records = records
@@ -256,7 +260,7 @@ class NeRF:
     def _alloc_workspace(self):
         lib = _lib.load()
         rows = self.ray_chunks * (self.n_coarse + self.n_fine)
-        need = lib.knerf_workspace_bytes(C.byref(self.cfg), rows, self._prec, int(self.is_training))
+        need = lib.knerf_workspace_bytes(C.byref(self.cfg), rows, self._prec_train, int(self.is_training))
         if need < 0:
             raise _lib.KnerfError("knerf_workspace_bytes: " + lib.knerf_last_error().decode())
         self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)

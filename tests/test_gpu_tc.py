@@ -274,7 +274,7 @@ def test_tc_training_kernels_are_bit_reproducible(R, S, records):
             gbuf = torch.zeros_like(m.fine.params)
             _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
                       R, S, m._prec_train, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
-            nbytes = int(lib.knerf_workspace_bytes(C.byref(m.cfg), R * S, m._prec, 1))
+            nbytes = int(lib.knerf_workspace_bytes(C.byref(m.cfg), R * S, m._prec_train, 1))
             # skip the fp32 X scratch at the head of the workspace (atomics)
             res.append((out.clone(), inf.clone(), m._ws.view(torch.uint8)[256 * 1024:nbytes].clone(), gbuf.clone()))
     a, b = res

@@ -67,6 +67,8 @@ def main(argv=None, multi_gpu=True):
     parser.add_argument('--log_freq', type=int, default=5 if multi_gpu else 1)
     parser.add_argument('--verbose', action='store_true')
     parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_tc'])
+    parser.add_argument('--records', type=str, default='fp8', choices=['fp8', 'bf16'],
+                        help='bf16 mode: format of the activation / gradient records kept for the weight gradients')
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO,
                         format='%(asctime)s | %(name)s | %(levelname)s | %(message)s')
@@ -95,7 +97,8 @@ def main(argv=None, multi_gpu=True):
         logging.info("Loading the latest logged model")
     nerf = NeRF(n_coarse=args.num_coarse_samples, n_fine=args.num_fine_samples, pos_emb_xyz=args.pos_emb_xyz,
                 pos_emb_dir=args.pos_emb_dir, n_layers=args.num_layers, dense_units=args.num_units,
-                skip_layer=args.skip_layer, model_path=model_path, precision=args.precision, strategy=strategy)
+                skip_layer=args.skip_layer, model_path=model_path, precision=args.precision, strategy=strategy,
+                records=args.records)
     log_dir = os.path.join(args.log_dir, args.name)
     if strategy is not None and strategy.rank != 0:
         log_dir = os.path.join(log_dir, f"rank{strategy.rank}")   # one writer per directory
