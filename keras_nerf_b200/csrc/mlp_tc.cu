@@ -277,41 +277,55 @@ __device__ __forceinline__ float* head_smem(uint8_t* xs) { return reinterpret_ca
 // (__noinline__: one body for all eight layers keeps the kernel below the I-cache thrash point.)
 // rec8 (fp8 records): the tile's saved activation record goes to HBM from here, 16 columns per 16-byte vector,
 // rounded from the fp32 accumulator -- no copy of the operand tile, no hand-shake with a store warp.
+// one 32-column group of epi_hidden: v = the accumulator values (already waited for)
+template <bool TRAIN, bool REC8>
+__device__ __forceinline__ void epi_hidden_group(const uint32_t (&v)[32], int gI, uint8_t* __restrict__ hs, int h, int r,
+                                                 uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rec8) {
+  const int col0 = h * 128 + gI * 32;
+  uint32_t mbits = 0u;
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
+    const uint4 pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
+                                pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
+    if (TRAIN) {
+      // ReLU' bits (tc_layout.cuh kRecMask).  The packed halves are non-negative, so half + 0x7fff has its msb set
+      // exactly when the half is > 0 (no carry between the halves); one prmt with sign replication turns the four
+      // flags of a word PAIR into four 0x00 / 0xff bytes, one LOP3 files bit q of every byte: 2 ALU-pipe
+      // instructions per pair where HSET2 + LOP3 per word were 4 (forward, training: 1.09 -> 1.04 ns per sample).
+      const uint32_t u0 = prmt(pk.x + 0x7fff7fffu, pk.y + 0x7fff7fffu, 0xFDB9u);
+      const uint32_t u1 = prmt(pk.z + 0x7fff7fffu, pk.w + 0x7fff7fffu, 0xFDB9u);
+      mbits |= u0 & (0x01010101u << (2 * c8));
+      mbits |= u1 & (0x01010101u << (2 * c8 + 1));
+    }
+    // next layer's A operand, in place; with bf16 records also the saved record (stored to HBM by warp 10)
+    *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
+  }
+  if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
+  if (TRAIN && REC8 && rec8 != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float* x = reinterpret_cast<const float*>(&v[16 * k]);
+      const uint4 q = make_uint4(pack_e4m3x4_relu(x[0], x[1], x[2], x[3]), pack_e4m3x4_relu(x[4], x[5], x[6], x[7]),
+                                 pack_e4m3x4_relu(x[8], x[9], x[10], x[11]),
+                                 pack_e4m3x4_relu(x[12], x[13], x[14], x[15]));
+      __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + k) * kChunkA + r * 16), q);
+    }
+  }
+}
+
 template <bool TRAIN, bool REC8>
 __device__ __noinline__ void epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs, int h, int r,
                                         uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rec8) {
+  // (measured and dropped: a second accumulator group in flight, so that the TMEM load of the next 32 columns runs under
+  //  the conversion of the current ones, and IMADs instead of integer adds for the flag additions -- no change in the
+  //  kernel's time, which at this point moves with the power cap more than with the instruction count)
 #pragma unroll 1
   for (int gI = 0; gI < 4; ++gI) {
-    const int col0 = h * 128 + gI * 32;
     uint32_t v[32];
-    tmem_ld32_issue(tacc + col0, v);
+    tmem_ld32_issue(tacc + h * 128 + gI * 32, v);
     tmem_ld32_wait(v);
-    uint32_t mbits = 0u;
-#pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-      const float* x = reinterpret_cast<const float*>(&v[c8 * 8]);
-      const uint4 pk = make_uint4(pack_bf16x2_relu(x[0], x[1]), pack_bf16x2_relu(x[2], x[3]),
-                                  pack_bf16x2_relu(x[4], x[5]), pack_bf16x2_relu(x[6], x[7]));
-      if (TRAIN) {   // HSET2 gives 0xffff per positive half: AND with (bit k | bit 16+k) picks the two bits
-        mbits |= bf16x2_gt0_mask(pk.x) & (0x00010001u << (c8 * 4 + 0));
-        mbits |= bf16x2_gt0_mask(pk.y) & (0x00010001u << (c8 * 4 + 1));
-        mbits |= bf16x2_gt0_mask(pk.z) & (0x00010001u << (c8 * 4 + 2));
-        mbits |= bf16x2_gt0_mask(pk.w) & (0x00010001u << (c8 * 4 + 3));
-      }
-      // next layer's A operand, in place; when training also the saved record (stored to HBM by warp 10)
-      *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
-    }
-    if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
-    if (TRAIN && REC8 && rec8 != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float* x = reinterpret_cast<const float*>(&v[16 * k]);
-        const uint4 q = make_uint4(pack_e4m3x4_relu(x[0], x[1], x[2], x[3]), pack_e4m3x4_relu(x[4], x[5], x[6], x[7]),
-                                   pack_e4m3x4_relu(x[8], x[9], x[10], x[11]),
-                                   pack_e4m3x4_relu(x[12], x[13], x[14], x[15]));
-        __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + k) * kChunkA + r * 16), q);
-      }
-    }
+    epi_hidden_group<TRAIN, REC8>(v, gI, hs, h, r, mask_out, rec8);
   }
 }
 

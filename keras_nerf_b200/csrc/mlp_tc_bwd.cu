@@ -33,12 +33,12 @@ namespace {
 // 2: dZ_l = dH * ReLU'(h_l), l = 6..1;  3: dZ0, the last step: feeds no further GEMM, so it goes to HBM directly
 // (dst = record or nullptr) and must NOT touch hs[tl], which the other half-row thread of this row may already be
 // rebuilding for the next tile.  KIND < 3: dst = hs[tl], the next A operand and (via warp 10) the dZ record.
-// mb = this thread's ReLU' bits (4 x 32 columns; bit k -> low half of word k, 16+k -> high half).
+// mb = this thread's ReLU' bits (4 x 32 columns; bit 8 t + q = column 4 q + t of the group).
 // REC8 (fp8 records): the dZ record leaves from here as e5m2(dZ * scale), 16 columns per 16-byte vector (rec8, nullptr
 // for a padding tile); dst is only the next A operand then (unused for KIND 3).
 template <int KIND, bool REC8>
 __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst, int h, int r, uint4 mbv, float dsig,
-                                       const float* __restrict__ wsig, uint8_t* __restrict__ rec8, float scale) {
+                                       const float* __restrict__ wsig, uint8_t* __restrict__ rec8) {
   const uint32_t mb[4] = {mbv.x, mbv.y, mbv.z, mbv.w};   // by value: no local memory (no L1 on this SM)
 #pragma unroll
   for (int gI = 0; gI < 4; ++gI) {
@@ -64,13 +64,16 @@ __device__ __noinline__ void epi_dgrad(uint32_t tacc, uint8_t* __restrict__ dst,
       }
       uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                             pack_bf16x2(x[6], x[7]));
-      const uint32_t bits = mb[gI] >> (c8 * 4);
-      const uint32_t m0 = (bits & 0x00010001u) * 0xffffu, m1 = ((bits >> 1) & 0x00010001u) * 0xffffu,
-                     m2 = ((bits >> 2) & 0x00010001u) * 0xffffu, m3 = ((bits >> 3) & 0x00010001u) * 0xffffu;
-      pk.x &= m0; pk.y &= m1; pk.z &= m2; pk.w &= m3;
-      if (REC8) {   // byte masks of columns (0,1,2,3) / (4,5,6,7) from the half-word masks
-        q8[2 * c8] = pack_e5m2x4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale) & __byte_perm(m0, m1, 0x6420);
-        q8[2 * c8 + 1] = pack_e5m2x4(x[4] * scale, x[5] * scale, x[6] * scale, x[7] * scale) & __byte_perm(m2, m3, 0x6420);
+      // ReLU' of columns 4q .. 4q+3 (q = 2 c8, 2 c8 + 1): bit q of bytes 0..3 of mb (tc_layout.cuh kRecMask).  Shifted left
+      // by 7 - q they are the four byte msbs, and ONE prmt with sign replication expands two of them to a half-word
+      // mask (the shift is an IMAD on the FMA pipe; the epilogue is bound by the half-rate ALU pipe)
+      const uint32_t ta = mb[gI] << (7 - 2 * c8), tb = mb[gI] << (6 - 2 * c8);
+      pk.x &= prmt(ta, 0u, 0x9988u); pk.y &= prmt(ta, 0u, 0xBBAAu);
+      pk.z &= prmt(tb, 0u, 0x9988u); pk.w &= prmt(tb, 0u, 0xBBAAu);
+      if (REC8) {   // byte masks of columns (0,1,2,3) / (4,5,6,7): the same flag bits of two words.  (The chain runs on
+                    // gradients that already carry the record scale -- see the prologue -- so there is no multiply here.)
+        q8[2 * c8] = pack_e5m2x4(x[0], x[1], x[2], x[3]) & prmt(ta, 0u, 0xBA98u);
+        q8[2 * c8 + 1] = pack_e5m2x4(x[4], x[5], x[6], x[7]) & prmt(tb, 0u, 0xBA98u);
         if (KIND < 3) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
       } else {
         if (KIND < 3 || dst != nullptr) *reinterpret_cast<uint4*>(dst + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
@@ -173,7 +176,10 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       const bool active = tile < n_tiles;
       float4 dp = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < M) dp = d_pre[g];
-      if (tl == 0) dsig_keep0 = dp.w; else dsig_keep1 = dp.w;
+      // fp8 records: the whole chain runs on gradients times the record scale (a power of two: the same mantissas, so
+      // every dZ is the same number times 2^k), and the e5m2 records need no multiply in the epilogues
+      const float4 dq = REC8 ? make_float4(dp.x * scale, dp.y * scale, dp.z * scale, dp.w * scale) : dp;
+      if (tl == 0) dsig_keep0 = dq.w; else dsig_keep1 = dq.w;
       uint8_t* dz_t = dz + tile * kDB;
       if (active && !REC8) {
         const uint4 pk = (h == 0) ? make_uint4(pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u)
@@ -182,7 +188,7 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
       }
       if (active && REC8 && h == 0)   // one 16-column chunk: (d rgb_pre, d sigma_pre) * scale, then zeros
         *reinterpret_cast<uint4*>(dz_t + kDz8P + r * 16) =
-            make_uint4(pack_e5m2x4(dp.x * scale, dp.y * scale, dp.z * scale, dp.w * scale), 0u, 0u, 0u);
+            make_uint4(pack_e5m2x4(dq.x, dq.y, dq.z, dq.w), 0u, 0u, 0u);
       if (h == 0) {   // bias gradients of the two heads: db_rgb = sum d(rgb_pre), db_sigma = sum d(sigma_pre)
         const float s0 = warp_sum(dp.x), s1 = warp_sum(dp.y), s2 = warp_sum(dp.z), s3 = warp_sum(dp.w);
         if (lane == 0) {
@@ -201,14 +207,14 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
         // rgb kernel rows col..col+7: 24 consecutive floats, 16-byte aligned (shared memory, broadcast reads)
         const float4* w4 = reinterpret_cast<const float4*>(wrgb + col * 3);
         const float4 a0 = w4[0], a1 = w4[1], a2 = w4[2], a3 = w4[3], a4 = w4[4], a5 = w4[5];
-        x[0] = dp.x * a0.x + dp.y * a0.y + dp.z * a0.z;
-        x[1] = dp.x * a0.w + dp.y * a1.x + dp.z * a1.y;
-        x[2] = dp.x * a1.z + dp.y * a1.w + dp.z * a2.x;
-        x[3] = dp.x * a2.y + dp.y * a2.z + dp.z * a2.w;
-        x[4] = dp.x * a3.x + dp.y * a3.y + dp.z * a3.z;
-        x[5] = dp.x * a3.w + dp.y * a4.x + dp.z * a4.y;
-        x[6] = dp.x * a4.z + dp.y * a4.w + dp.z * a5.x;
-        x[7] = dp.x * a5.y + dp.y * a5.z + dp.z * a5.w;
+        x[0] = dq.x * a0.x + dq.y * a0.y + dq.z * a0.z;
+        x[1] = dq.x * a0.w + dq.y * a1.x + dq.z * a1.y;
+        x[2] = dq.x * a1.z + dq.y * a1.w + dq.z * a2.x;
+        x[3] = dq.x * a2.y + dq.y * a2.z + dq.z * a2.w;
+        x[4] = dq.x * a3.x + dq.y * a3.y + dq.z * a3.z;
+        x[5] = dq.x * a3.w + dq.y * a4.x + dq.z * a4.y;
+        x[6] = dq.x * a4.z + dq.y * a4.w + dq.z * a5.x;
+        x[7] = dq.x * a5.y + dq.y * a5.z + dq.z * a5.w;
         const uint4 pk = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                                     pack_bf16x2(x[6], x[7]));
         const int off = (col >> 3) * kChunkA + r * 16;
@@ -247,9 +253,9 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           const uint32_t tacc = tmem + lane_base + tl * 256;
           const uint4 mbv = make_uint4(mb[0], mb[1], mb[2], mb[3]);
           uint8_t* out8 = (REC8 && active) ? out : nullptr;
-          if (b == 0) epi_dgrad<1, REC8>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig, out8, scale);
-          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2, REC8>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr, out8, scale);
-          else epi_dgrad<3, REC8>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr, out8, scale);
+          if (b == 0) epi_dgrad<1, REC8>(tacc, sm.hs[tl], h, r, mbv, dsig, wsig, out8);
+          else if (b + 1 < BwdProg::kSteps) epi_dgrad<2, REC8>(tacc, sm.hs[tl], h, r, mbv, 0.f, nullptr, out8);
+          else epi_dgrad<3, REC8>(tacc, active ? out : nullptr, h, r, mbv, 0.f, nullptr, out8);
           if (b + 1 < BwdProg::kSteps) {
             a_ready_arrive(tl);
           } else {

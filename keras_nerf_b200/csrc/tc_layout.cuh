@@ -125,7 +125,10 @@ constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
 //  + b' (x) sum d(rgb_pre) comes from three columns the weight-gradient kernel computes anyway -- tc_finish_kernel)
 constexpr int kRecMask = kRecH0 + 8 * kHSBytes;    // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
 constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns h*128 + g*32 + (0..31) of row r;
-                                                   //   bit i = column 2i, bit 16+i = column 2i+1 (bf16x2 packing order)
+                                                   //   bit 8 t + q = column 4 q + t (q = 0..7, t = 0..3): byte t holds one
+                                                   //   column of every group of four, so that a shift by 7 - q parks the
+                                                   //   four flags of columns 4q..4q+3 in the byte msbs, where one prmt with
+                                                   //   sign replication expands them to byte / half-word masks (dgrad)
 constexpr int kRecBytes = kRecMask + 8 * kMaskLayerBytes;   // 576 KB per 128 samples
 // pre-activation gradients written by the dgrad kernel for the weight-gradient GEMMs:
 constexpr int kDzZ0 = 0;                           // dZ0..dZ7     8 x 64 KB

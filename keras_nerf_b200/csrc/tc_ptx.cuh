@@ -265,6 +265,13 @@ __device__ __forceinline__ float2 e5m2x2_hi(uint32_t w) {
   const uint32_t h = __byte_perm(w, 0u, 0x3424);
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
+// prmt.b32 in its default mode: a selector nibble with bit 3 set yields the SIGN of the selected byte replicated over
+// the byte (0x00 / 0xff) -- one instruction turns flag bits parked in byte msbs into byte / half-word masks
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 
