@@ -99,6 +99,18 @@ def test_comm_entry_points_validate_arguments(lib):
     base = L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32, 1)
     assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32 | lib.TC_ORDERED | lib.BWD_DGRAD_ONLY, 1) == base
     assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32_TC, 1) > base       # + the split weight operand blobs
+    # ... except KNERF_REC_FP8, which halves the training records of the bf16 mode (and nothing else)
+    rows = 128 * 1000
+    bf = L.knerf_workspace_bytes(C.byref(cfg), rows, lib.BF16, 1)
+    f8 = L.knerf_workspace_bytes(C.byref(cfg), rows, lib.BF16 | lib.REC_FP8, 1)
+    assert (bf - f8) == 1000 * ((576 + 548) - (304 + 258)) * 1024                    # per 128-sample tile, tc_layout.cuh
+    assert L.knerf_workspace_bytes(C.byref(cfg), rows, lib.BF16 | lib.REC_FP8, 0) == L.knerf_workspace_bytes(
+        C.byref(cfg), rows, lib.BF16, 0)
+    assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32 | lib.REC_FP8, 1) == base
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "knerf.h")).read()
+    for name, val in (("KNERF_TC_ORDERED", lib.TC_ORDERED), ("KNERF_BWD_DGRAD_ONLY", lib.BWD_DGRAD_ONLY),
+                      ("KNERF_BWD_WGRAD_ONLY", lib.BWD_WGRAD_ONLY), ("KNERF_REC_FP8", lib.REC_FP8)):
+        assert int(re.search(rf"#define {name} (0x[0-9a-fA-F]+)", hdr).group(1), 16) == val
 
 
 def test_product_path_has_no_cpu_fallback(lib):
