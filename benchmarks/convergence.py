@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--records", default="fp8", choices=["fp8", "bf16"])
     ap.add_argument("--epochs", type=int, default=30)
     ap.add_argument("--img_wh", type=int, default=100)
     ap.add_argument("--views", type=int, default=24)
@@ -31,7 +32,7 @@ def main():
     data = write_nerf_synthetic_like(os.path.join(tmp, "scene"), image_wh=2 * a.img_wh, n_train=a.views, n_val=2, n_test=4)
     argv = ["--name", "ball", "--data_dir", data, "--img_wh", str(a.img_wh), "--batch_size", "1", "--ray_chunks",
             str(a.ray_chunks or a.img_wh * a.img_wh), "--log_dir", os.path.join(tmp, "logs"), "--model_dirs", os.path.join(tmp, "model"),
-            "--log_freq", str(max(a.epochs // 3, 1)), "--precision", a.precision, "--num_epochs", str(a.epochs)]
+            "--log_freq", str(max(a.epochs // 3, 1)), "--precision", a.precision, "--records", a.records, "--num_epochs", str(a.epochs)]
     if a.white_bg:
         argv.append("--white_bg")
     t0 = time.time()
