@@ -141,6 +141,7 @@ struct Model {
 };
 
 int build_model(const knerf_config* cfg, Model* m);
-bool is_flagship(const Model& m);  // 8 x 256, skip 4, L_xyz <= 10, L_dir <= 4: the shapes the fused bf16 path implements
+bool is_flagship(const Model& m);  // the shapes the fused bf16 path implements = tc_chain_map succeeds (api.cu)
+bool tc_chain_map(const Model& m, int chain_map[8]);
 
 }  // namespace knerf

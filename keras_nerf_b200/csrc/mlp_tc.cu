@@ -3,7 +3,8 @@
 // heads into the epilogue, so per-sample activations never round-trip through HBM at inference
 // (keras_nerf/model/nerf/mlp.py:29-50 + keras_nerf/model/nerf/utils.py:176-210).
 //
-// Flagship shape only (8x256, skip 4, L = 10/4); other shapes run the fp32 SIMT path.
+// 256-wide models of up to eight layers with at most one skip concat, L_xyz <= 10, L_dir <= 4 (csrc/api.cu tc_chain_map,
+// tc_layout.cuh TcParams); the Python shim runs other shapes in the fp32_tc mode.
 //
 // Forward kernel (persistent CTA pairs, 384 threads per CTA; roles in tc_roles.cuh / tc_roles2.cuh):
 //   warp 0      TMA producer: streams this CTA's half of the pre-packed bf16 weight blob, K = 64 stages, 4-slot ring
@@ -34,8 +35,9 @@ namespace {
 // B operand element of forward step s < 8 at reduction index k (hs part first, then the encoding part), output n
 __device__ __forceinline__ float fwd_weight(const float* __restrict__ params, const TcParams& P, int s, int k, int n) {
   const int L = s, kh = FwdProg::nk_h(s) * kKStage;
-  const int fan_in = (L == 0) ? P.dx : (L == 5) ? 256 + P.dx : 256;
+  const int fan_in = (L == 0) ? P.dx : (L == 5 && P.x5) ? 256 + P.dx : 256;
   const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
+  if (P.w_off[L] < 0) return row == n ? 1.f : 0.f;   // identity layer of the embedding
   return row < fan_in ? params[P.w_off[L] + (int64_t)row * 256 + n] : 0.f;
 }
 // W' = W_f W_g[:256] [256,128] and its bias b_f W_g[:256] + b_g [128] in fp32 (tc_layout.cuh), one thread per element
@@ -67,6 +69,7 @@ __device__ __forceinline__ float fold_bias(const float* __restrict__ params, con
 __device__ __forceinline__ float bwd_weight(const float* __restrict__ params, const TcParams& P,
                                             const float* __restrict__ fold, int b, int k, int n) {
   if (b == 0) return fold[n * 128 + k];
+  if (P.w_off[BwdProg::layer(b)] < 0) return n == k ? 1.f : 0.f;   // identity layer of the embedding
   return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * 256 + k];
 }
 
@@ -99,7 +102,8 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
       const int cta = rem / pb, r2 = rem - cta * pb;
       const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
       if (cb == 1)
-        w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, fold, cta * half + nl) : params[P.b_off[s] + cta * half + nl]);
+        w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, fold, cta * half + nl)
+                                       : (P.b_off[s] < 0 ? 0.f : params[P.b_off[s] + cta * half + nl]));
     }
     *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
     float v = 0.f;
     if (blk < 12) {
       const int fo = (blk == 8) ? 1 : (blk == 10) ? 128 : (blk == 11) ? 3 : 256;
-      if (j < fo) v = params[P.b_off[blk] + j];
+      if (j < fo && P.b_off[blk] >= 0) v = params[P.b_off[blk] + j];
     } else if (blk == 12) {
       v = params[P.w_off[8] + j];                       // sigma kernel [256,1]
     } else {
@@ -536,14 +540,21 @@ int64_t tc_workspace_bytes(const Model& m, int64_t rows, bool training, bool rec
 
 TcParams tc_make_params(const Model& m) {
   TcParams P;
-  for (int i = 0; i < 12; ++i) { P.w_off[i] = m.L[i].w_off; P.b_off[i] = m.L[i].b_off; }
+  int map[8];
+  tc_chain_map(m, map);   // (callers have checked is_flagship)
+  for (int c = 0; c < 8; ++c) {
+    P.w_off[c] = map[c] < 0 ? -1 : m.L[map[c]].w_off;
+    P.b_off[c] = map[c] < 0 ? -1 : m.L[map[c]].b_off;
+  }
+  for (int i = 0; i < 4; ++i) { P.w_off[8 + i] = m.L[m.n_layers + i].w_off; P.b_off[8 + i] = m.L[m.n_layers + i].b_off; }
+  P.x5 = (map[5] >= 0 && m.L[map[5]].k_x > 0) ? 1 : 0;
   P.dx = m.dx;
   P.dd = m.dd;
   return P;
 }
 
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_weights: packed must be 16-byte aligned");
   fold_kernel<<<257, 128, 0, st>>>(params, tc_make_params(m), reinterpret_cast<float*>((uint8_t*)packed + kFoldOff));
   KN_LAUNCH_CHECK();
@@ -556,7 +567,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
                int64_t R, int S, bool training, bool ordered_issue, bool rec8, float* rgbsigma, char* ws,
                int64_t ws_bytes, cudaStream_t st) {
   (void)params;
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   const int64_t M = R * S;
   if (training && ws_bytes < tc_workspace_bytes(m, M, true, rec8))
     return fail(KNERF_ERR_WORKSPACE, "tc_forward: workspace %lld < %lld bytes", (long long)ws_bytes,

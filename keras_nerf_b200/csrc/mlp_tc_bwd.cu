@@ -309,6 +309,20 @@ struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUni
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
+// (P: identity layers of the embedding -- w_off < 0 -- keep their tasks, so that the item layout does not depend on the
+//  model, but flush nothing: row_limit 0, no bias gradient)
+static void mask_identity_tasks(WTaskTable& T, const TcParams& P) {
+  for (int k = 0; k < kNumTasks; ++k) {
+    WTask& t = T.t[k];
+    for (int gi = 0; gi < t.n_groups; ++gi) {
+      const int l = t.g[gi].layer;
+      if (l >= 0 && l < 8 && (P.w_off[l] < 0 || (l == 5 && t.g[gi].row_base == 256 && !P.x5))) t.g[gi].row_limit = 0;
+    }
+    for (int u = 0; u < t.n_units; ++u)
+      if (t.u[u].bias_layer >= 0 && P.b_off[t.u[u].bias_layer] < 0) t.u[u].bias_layer = -1;
+  }
+}
+
 static WTaskTable build_task_table(int dx, int dd) {
   WTaskTable T{};
   int n = 0;
@@ -787,7 +801,7 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
 // parts: which of the backward kernels to launch (bit 0 dgrad, bit 1 wgrad + finish; KNERF_BWD_*_ONLY)
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, int parts, bool rec8, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements the 8 x 256 / skip 4 model with L_xyz <= 10, L_dir <= 4 only");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
   if (ws_bytes < tc_workspace_bytes(m, M, true, rec8))
@@ -831,7 +845,8 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   }
   if (parts & 2) {
     // ~3 KB, passed by value as a __grid_constant__
-    const WTaskTable h_table = rec8 ? build_task_table8(m.dx, m.dd) : build_task_table(m.dx, m.dd);
+    WTaskTable h_table = rec8 ? build_task_table8(m.dx, m.dd) : build_task_table(m.dx, m.dd);
+    mask_identity_tasks(h_table, P);
     // items = 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 178 -> 217 + 36 + 43 = 296 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(rec8 ? kSlabs8 : 31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);

@@ -1,5 +1,6 @@
 // Shapes, step tables and HBM layouts shared by the tcgen05 forward (mlp_tc.cu) and backward
-// (mlp_tc_bwd.cu) kernels.  Flagship model only: 8 x 256, skip 4, L = 10 / 4.
+// (mlp_tc_bwd.cu) kernels.  ONE program -- eight 256-wide layers, the encoding concatenated in front of layer 5 -- into
+// which the models csrc/api.cu tc_chain_map accepts are embedded (fewer layers: identity layers; fewer frequencies: zero rows).
 #pragma once
 
 #include <stdint.h>
@@ -108,7 +109,10 @@ constexpr int kBwdPairOff = kFwdPairOff + PairLayout<FwdProg>::kBytes;
 constexpr int kPackedBytes = kBwdPairOff + PairLayout<BwdProg>::kBytes;
 
 struct TcParams {
-  int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer
+  int64_t w_off[12], b_off[12];   // float offsets into the flat Keras-order parameter buffer, by CHAIN layer (0..7 hidden,
+                                  // 8..11 sigma / features / rgb_features / rgb); -1 = an identity layer of the embedding
+                                  // (api.cu tc_chain_map): kernel I, bias 0, gradients not flushed
+  int x5;                         // chain layer 5 takes the [h, x] concat (else its encoding rows are zero)
   int dx, dd;                     // widths of the encodings the model uses: 3 + 6 L_xyz <= 63, 3 + 6 L_dir <= 27.  PE_L is a
                                   // prefix of PE_10 / PE_4 (utils.py:176-186 appends one sin / cos block per frequency), so a
                                   // model with fewer frequencies runs on the same kernels: the operand keeps all 63 / 27

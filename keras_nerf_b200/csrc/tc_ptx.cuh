@@ -222,12 +222,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-// per-half 0xffff where the bf16 value is > 0 (HSET2.BF16.GT): AND-mask for ReLU'
-__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t p) {
-  uint32_t m;
-  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(p), "r"(0u));
-  return m;
-}
 // four fp32 -> four fp8 bytes (byte i = value i), round to nearest, saturating to the largest finite value
 __device__ __forceinline__ uint32_t pack_e4m3x4_relu(float a, float b, float c, float d) {
   uint32_t r;

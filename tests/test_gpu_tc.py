@@ -465,3 +465,103 @@ def test_tc_fp8_records_vs_bf16_records():
             print(f"{name:13s} {'kernel' if n > fo else 'bias  '} rel {rel:.4f}")
             assert rel <= 1e-2, name
             off += n
+
+
+DEPTHS = [(6, 4), (6, 3), (4, 4), (7, 4), (8, 8), (2, 4), (1, 4)]   # (n_layers, skip_layer) the chain kernels can embed
+
+
+@pytest.mark.parametrize("n_layers,skip", DEPTHS)
+def test_tc_other_depths_vs_fp32(n_layers, skip):
+    """--num_layers / --skip_layer (train.py:26-28): models of up to eight 256-wide layers with at most one skip concat
+    run on the same fused kernels -- the missing chain layers are identity layers, which are exact behind a ReLU
+    (csrc/api.cu tc_chain_map).  Forward and weight gradients against the fp32 mode, as for the default model."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S = 512, 192
+    ms = []
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == prec                       # no fall-back
+        ms.append(m)
+    assert torch.equal(ms[0].fine.params, ms[1].fine.params)
+    o, d, t, tgt = _rays(R, S, seed=17 + n_layers)
+    grads, outs = {}, {}
+    for m in ms:
+        out = _fwd(m, m.fine, o, d, t, True)
+        outs[m.precision] = out
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec_train, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        grads[m.precision] = gbuf.cpu()
+    ia, ib = _composite(outs["fp32"], t), _composite(outs["bf16"], t)
+    assert float((ia - ib).abs().max()) <= 2e-3
+    cfg = O.NerfConfig(n_layers=n_layers, skip_layer=skip)
+    a, b = grads["fp32"], grads["bf16"]
+    assert a.numel() == O.param_count(cfg) and torch.isfinite(b).all()
+    off = 0
+    for name, fi, fo in O.layer_shapes(cfg):
+        for n in (fi * fo, fo):
+            x, y = a[off:off + n], b[off:off + n]
+            rel = float((x - y).norm() / x.norm().clamp_min(1e-30))
+            assert rel <= 4e-2, (name, rel)
+            off += n
+
+
+def test_tc_shallower_model_equals_default_model_with_identity_layers():
+    """Structure check of the embedding, free of rounding noise: a 6-layer / skip 4 model IS the default 8-layer model
+    whose layers 6 and 7 are identity layers (kernel I, bias 0) -- the bf16 forward output must be bit-identical and the
+    gradients of the shared layers equal up to the order of the atomic flushes."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S = 300, 192
+    mlp_mod.set_seed(7)
+    small = K.NeRF(precision="bf16", n_layers=6)
+    big = K.NeRF(precision="bf16")
+    for m in (small, big):
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == "bf16"
+    cs, cb = O.NerfConfig(n_layers=6), O.NerfConfig()
+    ps = small.fine.params.cpu()
+    ps = ps + 0.01 * torch.randn(ps.numel(), generator=torch.Generator().manual_seed(1))
+    pb = torch.zeros(O.param_count(cb))
+    shapes_s, shapes_b = O.layer_shapes(cs), O.layer_shapes(cb)
+    offs = lambda shapes: np.cumsum([0] + [fi * fo + fo for _, fi, fo in shapes])  # noqa: E731
+    os_, ob = offs(shapes_s), offs(shapes_b)
+    pairs = []                                           # (index in small, index in big)
+    for i, (name, fi, fo) in enumerate(shapes_s):
+        j = i if i < 6 else i + 2                        # hidden layers keep their place, the heads move up by two
+        assert shapes_b[j][1:] == (fi, fo), (name, shapes_b[j])
+        n = fi * fo + fo
+        pb[ob[j]:ob[j] + n] = ps[os_[i]:os_[i] + n]
+        pairs.append((int(os_[i]), int(ob[j]), n))
+    for j in (6, 7):
+        pb[ob[j]:ob[j] + 256 * 256] = torch.eye(256).flatten()
+    small.fine.params.copy_(ps.to(small.fine.params.device))
+    big.fine.params.copy_(pb.to(big.fine.params.device))
+    small._repack()
+    big._repack()
+    o, d, t, tgt = _rays(R, S, seed=11)
+    res = []
+    for m in (small, big):
+        out = _fwd(m, m.fine, o, d, t, True)
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec_train, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        res.append((out.cpu(), gbuf.cpu()))
+    (out_s, g_s), (out_b, g_b) = res
+    assert torch.equal(out_s, out_b)
+    for a, b, n in pairs:
+        x, y = g_s[a:a + n], g_b[b:b + n]
+        assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-12, (a, b, n)
