@@ -57,8 +57,8 @@ typedef enum knerf_oob_mode {
 
 typedef enum knerf_precision {
   KNERF_FP32 = 0, /* SIMT FFMA, fp32 end to end: the 1e-5 parity mode                   */
-  KNERF_BF16 = 1, /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation; 256-wide models of up to 8
-                   * layers with at most one skip concat (not into the heads), pos_emb_xyz <= 10,
+  KNERF_BF16 = 1, /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation; models of dense_units <= 256
+                   * (even), up to 8 layers, at most one skip concat (not into the heads), pos_emb_xyz <= 10,
                    * pos_emb_dir <= 4 (else KNERF_ERR_UNSUPPORTED) */
   KNERF_FP32_TC = 2 /* fp32-grade results ON the tensor cores: every fp32 operand is split into three bf16 values
                        (24 mantissa bits) and each product formed from its six leading bf16 x bf16 terms, fp32

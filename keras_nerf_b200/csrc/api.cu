@@ -62,13 +62,14 @@ int build_model(const knerf_config* cfg, Model* m) {
 // The fused bf16 chain kernels run ONE fixed program: eight 256-wide ReLU layers, the encoding concatenated in front of
 // chain layer 5, then the heads.  A model fits when it can be embedded in that program exactly:
 //  * encodings that are prefixes of PE_10 / PE_4 (unused columns get zero weights);
-//  * up to eight 256-wide layers with at most one layer that takes the skip concat (and not the heads): its layers
+//  * dense_units <= 256: the operands are zero-padded to 256 columns (relu(0) = 0 stays 0, its gradients are not flushed);
+//  * up to eight layers with at most one layer that takes the skip concat (and not the heads): its layers
 //    keep their order, the concat layer sits at chain layer 5, and the remaining chain layers are IDENTITY layers
 //    (kernel I, bias 0).  An identity layer behind a ReLU is exact, in fp32 and in bf16 alike: its input h >= 0 is
 //    already rounded, relu(I h) = h has the same bits, and backwards (dH [h > 0]) [h > 0] = dH [h > 0].
 // chain_map[c] = the model layer at chain layer c, -1 = identity.
 bool tc_chain_map(const Model& m, int chain_map[8]) {
-  if (!(m.U == 256 && m.n_layers >= 1 && m.n_layers <= 8 && !m.head_skip && m.cfg.pos_emb_xyz >= 0 &&
+  if (!(m.U >= 2 && m.U <= 256 && m.U % 2 == 0 && m.n_layers >= 1 && m.n_layers <= 8 && !m.head_skip && m.cfg.pos_emb_xyz >= 0 &&
         m.cfg.pos_emb_xyz <= 10 && m.cfg.pos_emb_dir >= 0 && m.cfg.pos_emb_dir <= 4 &&
         m.dx == 3 + 6 * m.cfg.pos_emb_xyz && m.dd == 3 + 6 * m.cfg.pos_emb_dir))
     return false;

@@ -34,31 +34,43 @@ namespace {
 // ---- weight packing --------------------------------------------------------------------------------------
 // B operand element of forward step s < 8 at reduction index k (hs part first, then the encoding part), output n
 __device__ __forceinline__ float fwd_weight(const float* __restrict__ params, const TcParams& P, int s, int k, int n) {
-  const int L = s, kh = FwdProg::nk_h(s) * kKStage;
-  const int fan_in = (L == 0) ? P.dx : (L == 5 && P.x5) ? 256 + P.dx : 256;
-  const int row = k < kh ? k : (kh > 0 ? 256 : 0) + (k - kh);
-  if (P.w_off[L] < 0) return row == n ? 1.f : 0.f;   // identity layer of the embedding
-  return row < fan_in ? params[P.w_off[L] + (int64_t)row * 256 + n] : 0.f;
+  const int L = s, kh = FwdProg::nk_h(s) * kKStage, U = P.U;
+  if (P.w_off[L] < 0) return (k < kh && k == n) ? 1.f : 0.f;   // identity layer of the embedding
+  if (n >= U) return 0.f;
+  int row;                                                      // row of the model's kernel [fan_in, U]
+  if (k < kh) {
+    if (k >= U) return 0.f;
+    row = k;
+  } else {
+    const int j = k - kh;                                       // encoding column
+    if (j >= P.dx || (L != 0 && !(L == 5 && P.x5))) return 0.f;
+    row = (kh > 0 ? U : 0) + j;
+  }
+  return params[P.w_off[L] + (int64_t)row * U + n];
 }
 // W' = W_f W_g[:256] [256,128] and its bias b_f W_g[:256] + b_g [128] in fp32 (tc_layout.cuh), one thread per element
 __global__ void __launch_bounds__(128) fold_kernel(const float* __restrict__ params, TcParams P, float* __restrict__ fold) {
-  const float* Wf = params + P.w_off[9];    // features      [256, 256]
-  const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
+  const int U = P.U, H = P.U / 2;
+  const float* Wf = params + P.w_off[9];    // features      [U, U]
+  const float* Wg = params + P.w_off[10];   // rgb_features  [U + dd, U/2]
   const int n = threadIdx.x, k = blockIdx.x;   // k = 256: the bias row
-  const float* row = k < 256 ? Wf + k * 256 : params + P.b_off[9];
-  float acc = k < 256 ? 0.f : params[P.b_off[10] + n];
+  float acc = 0.f;
+  if (n < H && (k < U || k == 256)) {
+    const float* row = k < 256 ? Wf + (int64_t)k * U : params + P.b_off[9];
+    acc = k < 256 ? 0.f : params[P.b_off[10] + n];
 #pragma unroll 8
-  for (int j = 0; j < 256; ++j) acc = fmaf(row[j], Wg[j * 128 + n], acc);
+    for (int j = 0; j < U; ++j) acc = fmaf(row[j], Wg[j * H + n], acc);
+  }
   fold[k * 128 + n] = acc;
 }
 // last forward step: reduction index k (h7, then the direction encoding), output column n
 __device__ __forceinline__ float fold_weight(const float* __restrict__ params, const TcParams& P,
                                              const float* __restrict__ fold, int k, int n) {
   if (n < 128) {
-    if (k >= 256) return (k - 256 < P.dd) ? params[P.w_off[10] + (int64_t)k * 128 + n] : 0.f;
+    if (k >= 256) return (k - 256 < P.dd && n < P.U / 2) ? params[P.w_off[10] + (int64_t)(P.U + k - 256) * (P.U / 2) + n] : 0.f;
     return fold[k * 128 + n];
   }
-  return (n == 128 && k < 256) ? params[P.w_off[8] + k] : 0.f;   // sigma kernel [256, 1]
+  return (n == 128 && k < P.U) ? params[P.w_off[8] + k] : 0.f;   // sigma kernel [U, 1]
 }
 __device__ __forceinline__ float fold_bias(const float* __restrict__ params, const TcParams& P,
                                            const float* __restrict__ fold, int n) {
@@ -70,7 +82,7 @@ __device__ __forceinline__ float bwd_weight(const float* __restrict__ params, co
                                             const float* __restrict__ fold, int b, int k, int n) {
   if (b == 0) return fold[n * 128 + k];
   if (P.w_off[BwdProg::layer(b)] < 0) return n == k ? 1.f : 0.f;   // identity layer of the embedding
-  return params[P.w_off[BwdProg::layer(b)] + (int64_t)n * 256 + k];
+  return (n < P.U && k < P.U) ? params[P.w_off[BwdProg::layer(b)] + (int64_t)n * P.U + k] : 0.f;
 }
 
 template <class Prog, bool FWD>
@@ -103,7 +115,7 @@ __device__ __forceinline__ void pack_pair(const float* __restrict__ params, cons
       const int cb = r2 / (half * 16), nl = (r2 - cb * half * 16) / 16;
       if (cb == 1)
         w[3] = pack_bf16x2(0.f, s == 8 ? fold_bias(params, P, fold, cta * half + nl)
-                                       : (P.b_off[s] < 0 ? 0.f : params[P.b_off[s] + cta * half + nl]));
+                                       : ((P.b_off[s] < 0 || cta * half + nl >= P.U) ? 0.f : params[P.b_off[s] + cta * half + nl]));
     }
     *reinterpret_cast<uint4*>(blob + byte) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -120,13 +132,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
     const int blk = i >> 8, j = i & 255;
     float v = 0.f;
     if (blk < 12) {
-      const int fo = (blk == 8) ? 1 : (blk == 10) ? 128 : (blk == 11) ? 3 : 256;
+      const int fo = (blk == 8) ? 1 : (blk == 10) ? P.U / 2 : (blk == 11) ? 3 : P.U;
       if (j < fo && P.b_off[blk] >= 0) v = params[P.b_off[blk] + j];
     } else if (blk == 12) {
-      v = params[P.w_off[8] + j];                       // sigma kernel [256,1]
+      if (j < P.U) v = params[P.w_off[8] + j];          // sigma kernel [U,1]
     } else {
       const int k = i - 13 * 256;
-      if (k < 384) v = params[P.w_off[11] + k];         // rgb kernel [128,3]
+      if (k < (P.U / 2) * 3) v = params[P.w_off[11] + k];   // rgb kernel [U/2,3]
     }
     aux[i] = v;
   }
@@ -548,13 +560,14 @@ TcParams tc_make_params(const Model& m) {
   }
   for (int i = 0; i < 4; ++i) { P.w_off[8 + i] = m.L[m.n_layers + i].w_off; P.b_off[8 + i] = m.L[m.n_layers + i].b_off; }
   P.x5 = (map[5] >= 0 && m.L[map[5]].k_x > 0) ? 1 : 0;
+  P.U = m.U;
   P.dx = m.dx;
   P.dd = m.dd;
   return P;
 }
 
 int tc_pack_weights(const Model& m, const float* params, void* packed, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements models of dense_units <= 256 (even), up to 8 layers, at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   KN_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_weights: packed must be 16-byte aligned");
   fold_kernel<<<257, 128, 0, st>>>(params, tc_make_params(m), reinterpret_cast<float*>((uint8_t*)packed + kFoldOff));
   KN_LAUNCH_CHECK();
@@ -567,7 +580,7 @@ int tc_forward(const Model& m, const float* params, const void* packed, const fl
                int64_t R, int S, bool training, bool ordered_issue, bool rec8, float* rgbsigma, char* ws,
                int64_t ws_bytes, cudaStream_t st) {
   (void)params;
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements models of dense_units <= 256 (even), up to 8 layers, at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   const int64_t M = R * S;
   if (training && ws_bytes < tc_workspace_bytes(m, M, true, rec8))
     return fail(KNERF_ERR_WORKSPACE, "tc_forward: workspace %lld < %lld bytes", (long long)ws_bytes,

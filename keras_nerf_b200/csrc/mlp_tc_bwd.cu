@@ -309,14 +309,27 @@ struct WTask { int n_units; WUnit u[kWMaxUnits]; int n_groups; WGroup g[kWMaxUni
 
 struct WTaskTable { WTask t[kNumTasks]; };
 
-// (P: identity layers of the embedding -- w_off < 0 -- keep their tasks, so that the item layout does not depend on the
-//  model, but flush nothing: row_limit 0, no bias gradient)
-static void mask_identity_tasks(WTaskTable& T, const TcParams& P) {
+// Fit the task table of the chain's fixed program to the model embedded in it (api.cu tc_chain_map).  Identity layers
+// (w_off < 0) keep their tasks, so that the item layout does not depend on the model, but flush nothing: row_limit 0,
+// no bias gradient.  A narrower model (U < 256) flushes only its own rows / columns, and the encoding rows of the
+// concat layer start at row U of its kernel.
+static void fit_tasks_to_model(WTaskTable& T, const TcParams& P) {
   for (int k = 0; k < kNumTasks; ++k) {
     WTask& t = T.t[k];
     for (int gi = 0; gi < t.n_groups; ++gi) {
-      const int l = t.g[gi].layer;
-      if (l >= 0 && l < 8 && (P.w_off[l] < 0 || (l == 5 && t.g[gi].row_base == 256 && !P.x5))) t.g[gi].row_limit = 0;
+      WGroup& g = t.g[gi];
+      const int l = g.layer;
+      if (g.mode == 0 && l >= 0 && l < 8) {
+        if (l == 5 && g.row_base == 256) {            // encoding rows of the concat layer
+          g.row_base = P.U;
+          if (!P.x5) g.row_limit = 0;
+        } else if (l > 0) {                           // hidden rows (layer 0's rows are encoding columns)
+          g.row_limit = std::max(0, std::min(g.row_limit, P.U - g.row_base));
+        }
+        if (P.w_off[l] < 0) g.row_limit = 0;
+      } else if (g.mode == 1) {                       // Y = h7^T d(rgb_pre) and the sigma kernel: rows of h7
+        g.row_limit = std::max(0, std::min(g.row_limit, P.U - g.row_base));
+      }
     }
     for (int u = 0; u < t.n_units; ++u)
       if (t.u[u].bias_layer >= 0 && P.b_off[t.u[u].bias_layer] < 0) t.u[u].bias_layer = -1;
@@ -656,9 +669,11 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
               a[e] += __shfl_xor_sync(0xffffffffu, a[e], 4);
             }
             if (fsub == 0) {
-              float* dst = grads + P.b_off[t.u[k].bias_layer] + t.u[k].bias_col0 + (REC8 ? fc * 16 + u * 8 : fc * 8);
+              const int c0 = t.u[k].bias_col0 + (REC8 ? fc * 16 + u * 8 : fc * 8);
+              float* dst = grads + P.b_off[t.u[k].bias_layer] + c0;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) atomicAdd(dst + e, a[e] * inv_scale);
+              for (int e = 0; e < 8; ++e)
+                if (c0 + e < P.U) atomicAdd(dst + e, a[e] * inv_scale);
             }
           }
           ++nb;
@@ -685,11 +700,12 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
             for (int i = 0; i < 32; ++i) v[i] *= inv_scale;
           }
           if (row < g.row_limit) {
-            if (g.mode == 0) {
-              const int ld = (g.layer == 10) ? 128 : 256;
-              float* dst = grads + P.w_off[g.layer] + (int64_t)(g.row_base + row) * ld + g.col_base + c0;
+            if (g.mode == 0) {   // kernel [fan_in, U] of a hidden layer: columns >= U belong to the padding
+              float* dst = grads + P.w_off[g.layer] + (int64_t)(g.row_base + row) * P.U + g.col_base + c0;
+              const int nv = P.U - (g.col_base + c0);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+              for (int i = 0; i < 32; ++i)
+                if (i < nv) atomicAdd(dst + i, v[i]);
             } else if (g.mode == 1) {
               atomicAdd(grads + P.w_off[8] + g.row_base + row, v[3]);
               float* dst = xbuf + kXOffY + (g.row_base + row) * 4;
@@ -725,24 +741,30 @@ tc_wgrad_kernel(const uint8_t* __restrict__ rec, const uint8_t* __restrict__ dz,
 constexpr int kFinF = 256 * 256, kFinG = 256 * 128, kFinBf = 256, kFinGd = 27 * 128, kFinBg = 128, kFinC = 128 * 3;   // (kFinGd: rows >= dd idle)
 constexpr int kFinTotal = kFinF + kFinG + kFinBf + kFinGd + kFinBg + kFinC;
 
-// the two 256 x 3 factors every output of tc_finish_kernel needs (one thread each; 0.3 M MAC)
+// the two U x 3 factors every output of tc_finish_kernel needs (one thread each; 0.3 M MAC)
+// (U = dense_units <= 256, H = U / 2: the kernels are [U, U], [U + dd, H], [H, 3] in the flat buffer; the scratch and the
+//  fold keep their 256 / 128 strides)
 __global__ void __launch_bounds__(256) tc_finish_prep_kernel(const float* __restrict__ params, TcParams P,
                                                              float* __restrict__ xbuf) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // < 2 * 256 * 3
   const int which = idx / 768, e = idx - which * 768, j = e / 3, c = e - j * 3;
+  const int U = P.U, H = P.U / 2;
   if (which > 1) return;
   const float* Wc = params + P.w_off[11];
-  float acc;
+  float acc = 0.f;
   if (which == 0) {
-    const float* w = params + P.w_off[10] + j * 128;
-    acc = 0.f;
-    for (int n = 0; n < 128; ++n) acc = fmaf(w[n], Wc[n * 3 + c], acc);
+    if (j < U) {
+      const float* w = params + P.w_off[10] + (int64_t)j * H;
+      for (int n = 0; n < H; ++n) acc = fmaf(w[n], Wc[n * 3 + c], acc);
+    }
     xbuf[kXOffT + j * 4 + c] = acc;
   } else {
-    const float* Wf = params + P.w_off[9];
-    const float* Y = xbuf + kXOffY;
-    acc = params[P.b_off[9] + j] * xbuf[kXOffS + c];
-    for (int i = 0; i < 256; ++i) acc = fmaf(Wf[i * 256 + j], Y[i * 4 + c], acc);
+    if (j < U) {
+      const float* Wf = params + P.w_off[9];
+      const float* Y = xbuf + kXOffY;
+      acc = params[P.b_off[9] + j] * xbuf[kXOffS + c];
+      for (int i = 0; i < U; ++i) acc = fmaf(Wf[(int64_t)i * U + j], Y[i * 4 + c], acc);
+    }
     xbuf[kXOffU + j * 4 + c] = acc;
   }
 }
@@ -751,47 +773,51 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
                                                         const float* __restrict__ xbuf, float* __restrict__ grads,
                                                         const float* __restrict__ fold) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* Wg = params + P.w_off[10];   // rgb_features  [283, 128]
-  const float* Wc = params + P.w_off[11];   // rgb           [128, 3]
+  const int U = P.U, H = P.U / 2;
+  const float* Wg = params + P.w_off[10];   // rgb_features  [U + dd, H]
+  const float* Wc = params + P.w_off[11];   // rgb           [H, 3]
   const float* Y = xbuf + kXOffY;
   const float* Yd = xbuf + kXOffYd;
   const float* T = xbuf + kXOffT;
-  const float* U = xbuf + kXOffU;
+  const float* Uf = xbuf + kXOffU;
   const float s3[3] = {xbuf[kXOffS], xbuf[kXOffS + 1], xbuf[kXOffS + 2]};
   if (idx < kFinF) {
     const int i = idx >> 8, j = idx & 255;
-    grads[P.w_off[9] + idx] += Y[i * 4] * T[j * 4] + Y[i * 4 + 1] * T[j * 4 + 1] + Y[i * 4 + 2] * T[j * 4 + 2];
+    if (i < U && j < U)
+      grads[P.w_off[9] + (int64_t)i * U + j] += Y[i * 4] * T[j * 4] + Y[i * 4 + 1] * T[j * 4 + 1] + Y[i * 4 + 2] * T[j * 4 + 2];
     return;
   }
   idx -= kFinF;
   if (idx < kFinG) {
     const int j = idx >> 7, n = idx & 127;
-    grads[P.w_off[10] + idx] += U[j * 4] * Wc[n * 3] + U[j * 4 + 1] * Wc[n * 3 + 1] + U[j * 4 + 2] * Wc[n * 3 + 2];
+    if (j < U && n < H)
+      grads[P.w_off[10] + (int64_t)j * H + n] += Uf[j * 4] * Wc[n * 3] + Uf[j * 4 + 1] * Wc[n * 3 + 1] + Uf[j * 4 + 2] * Wc[n * 3 + 2];
     return;
   }
   idx -= kFinG;
   if (idx < kFinBf) {
-    grads[P.b_off[9] + idx] += s3[0] * T[idx * 4] + s3[1] * T[idx * 4 + 1] + s3[2] * T[idx * 4 + 2];
+    if (idx < U) grads[P.b_off[9] + idx] += s3[0] * T[idx * 4] + s3[1] * T[idx * 4 + 1] + s3[2] * T[idx * 4 + 2];
     return;
   }
   idx -= kFinBf;
   if (idx < kFinGd) {
     const int i = idx >> 7, n = idx & 127;
-    if (i < P.dd)
-      grads[P.w_off[10] + 256 * 128 + idx] += Yd[i * 4] * Wc[n * 3] + Yd[i * 4 + 1] * Wc[n * 3 + 1] + Yd[i * 4 + 2] * Wc[n * 3 + 2];
+    if (i < P.dd && n < H)
+      grads[P.w_off[10] + (int64_t)(U + i) * H + n] += Yd[i * 4] * Wc[n * 3] + Yd[i * 4 + 1] * Wc[n * 3 + 1] + Yd[i * 4 + 2] * Wc[n * 3 + 2];
     return;
   }
   idx -= kFinGd;
   if (idx < kFinBg) {
-    grads[P.b_off[10] + idx] += s3[0] * Wc[idx * 3] + s3[1] * Wc[idx * 3 + 1] + s3[2] * Wc[idx * 3 + 2];
+    if (idx < H) grads[P.b_off[10] + idx] += s3[0] * Wc[idx * 3] + s3[1] * Wc[idx * 3 + 1] + s3[2] * Wc[idx * 3 + 2];
     return;
   }
   idx -= kFinBg;
   if (idx < kFinC) {
     const int k = idx / 3, c = idx - k * 3;
+    if (k >= H) return;
     float acc = fold[256 * 128 + k] * s3[c];
-    for (int j = 0; j < 256; ++j) acc = fmaf(fold[j * 128 + k], Y[j * 4 + c], acc);
-    for (int i = 0; i < P.dd; ++i) acc = fmaf(Wg[(256 + i) * 128 + k], Yd[i * 4 + c], acc);
+    for (int j = 0; j < U; ++j) acc = fmaf(fold[j * 128 + k], Y[j * 4 + c], acc);
+    for (int i = 0; i < P.dd; ++i) acc = fmaf(Wg[(int64_t)(U + i) * H + k], Yd[i * 4 + c], acc);
     grads[P.w_off[11] + idx] += acc;
   }
 }
@@ -801,7 +827,7 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const float* __restrict_
 // parts: which of the backward kernels to launch (bit 0 dgrad, bit 1 wgrad + finish; KNERF_BWD_*_ONLY)
 int tc_backward(const Model& m, const float* params, const void* packed, const float* d_pre, int64_t R, int S,
                 float* grads, char* ws, int64_t ws_bytes, int parts, bool rec8, cudaStream_t st) {
-  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
+  if (!is_flagship(m)) return fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements models of dense_units <= 256 (even), up to 8 layers, at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4");
   KN_CHECK_ARG(packed != nullptr, "KNERF_BF16 needs packed weights (knerf_pack_weights)");
   const int64_t M = R * S;
   if (ws_bytes < tc_workspace_bytes(m, M, true, rec8))
@@ -846,7 +872,7 @@ int tc_backward(const Model& m, const float* params, const void* packed, const f
   if (parts & 2) {
     // ~3 KB, passed by value as a __grid_constant__
     WTaskTable h_table = rec8 ? build_task_table8(m.dx, m.dd) : build_task_table(m.dx, m.dd);
-    mask_identity_tasks(h_table, P);
+    fit_tasks_to_model(h_table, P);
     // items = 2 x 148: 7 tasks of cost 128, 2 of cost 76, 1 of cost 178 -> 217 + 36 + 43 = 296 items for 31 slabs
     const int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(rec8 ? kSlabs8 : 31, n_tiles / 4));
     const int n_items = count_items(h_table, slabs);

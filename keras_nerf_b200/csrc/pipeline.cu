@@ -95,7 +95,7 @@ extern "C" int64_t knerf_packed_weight_bytes(const knerf_config* cfg) {
   if (build_model(cfg, &m) != KNERF_OK) return -1;
   const int64_t n = tc_packed_weight_bytes(m);
   if (n < 0)
-    fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements 256-wide models of up to 8 layers with at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4 (got %d x %d, skip %d, L=%d,%d)",
+    fail(KNERF_ERR_UNSUPPORTED, "KNERF_BF16 implements models of dense_units <= 256 (even), up to 8 layers, at most one skip concat (not into the heads), L_xyz <= 10, L_dir <= 4 (got %d x %d, skip %d, L=%d,%d)",
          m.n_layers, m.U, m.cfg.skip_layer, m.cfg.pos_emb_xyz, m.cfg.pos_emb_dir);
   return n;
 }

@@ -113,6 +113,9 @@ struct TcParams {
                                   // 8..11 sigma / features / rgb_features / rgb); -1 = an identity layer of the embedding
                                   // (api.cu tc_chain_map): kernel I, bias 0, gradients not flushed
   int x5;                         // chain layer 5 takes the [h, x] concat (else its encoding rows are zero)
+  int U;                          // dense_units of the model (even, <= 256): kernels are [fan_in, U] in the flat buffer (the
+                                  // rgb_features kernel [U + dd, U/2]); in the chain's 256-wide operands the columns / rows >= U
+                                  // are zero -- their activations are relu(0) = 0 -- and are never flushed
   int dx, dd;                     // widths of the encodings the model uses: 3 + 6 L_xyz <= 63, 3 + 6 L_dir <= 27.  PE_L is a
                                   // prefix of PE_10 / PE_4 (utils.py:176-186 appends one sin / cos block per frequency), so a
                                   // model with fewer frequencies runs on the same kernels: the operand keeps all 63 / 27

@@ -229,9 +229,9 @@ class NeRF:
             lib = _lib.load()
             nbytes = lib.knerf_packed_weight_bytes(C.byref(self.cfg))
             if nbytes <= 0:
-                # the fused bf16 chain kernels take 256-wide models of up to eight layers with at most one skip concat
-                # (not into the heads), --pos_emb_xyz <= 10 and --pos_emb_dir <= 4 (csrc/api.cu tc_chain_map); any other
-                # shape the reference's CLI accepts (--num_units, more layers / skips / frequencies) runs in the fp32_tc mode -- per-layer tcgen05 GEMMs for every layer whose width is a multiple of 64,
+                # the fused bf16 chain kernels take models of --num_units <= 256, up to eight layers with at most one skip
+                # concat (not into the heads), --pos_emb_xyz <= 10 and --pos_emb_dir <= 4 (csrc/api.cu tc_chain_map); any
+                # other shape the reference's CLI accepts (wider, more layers / skips / frequencies) runs in the fp32_tc mode -- per-layer tcgen05 GEMMs for every layer whose width is a multiple of 64,
                 # SIMT FFMA for the others -- and says so
                 logging.warning("precision='bf16' is not available for this model shape (%s); using precision="
                                 "'fp32_tc' (fp32-grade per-layer tensor-core GEMMs)",

@@ -107,7 +107,7 @@ def test_comm_entry_points_validate_arguments(lib):
     assert L.knerf_workspace_bytes(C.byref(cfg), rows, lib.BF16 | lib.REC_FP8, 0) == L.knerf_workspace_bytes(
         C.byref(cfg), rows, lib.BF16, 0)
     assert L.knerf_workspace_bytes(C.byref(cfg), 4096, lib.FP32 | lib.REC_FP8, 1) == base
-    # shapes the fused bf16 kernels take (csrc/api.cu tc_chain_map): <= 8 layers of 256 units, at most one skip concat,
+    # shapes the fused bf16 kernels take (csrc/api.cu tc_chain_map): <= 8 layers of <= 256 units, at most one skip concat,
     # not into the heads, no more than 10 / 4 encoding frequencies
     def packed(n_layers=8, units=256, skip=4, lx=10, ld=4):
         c = lib.Config(64, 128, lx, ld, n_layers, units, skip, 0, 0)
@@ -116,8 +116,9 @@ def test_comm_entry_points_validate_arguments(lib):
         assert packed(nl, 256, sk) == packed(), (nl, sk)
     for nl, sk in ((8, 3), (8, 5), (5, 4), (8, 2), (9, 4), (7, 3)):
         assert packed(nl, 256, sk) < 0, (nl, sk)
-    assert packed(units=128) < 0 and packed(units=512) < 0 and packed(lx=11) < 0 and packed(ld=5) < 0
-    assert packed(lx=6, ld=2) == packed() and b"256-wide" in L.knerf_last_error()
+    assert packed(units=128) == packed() and packed(units=64, n_layers=4, skip=2) == packed()   # zero-padded to 256
+    assert packed(units=512) < 0 and packed(units=258) < 0 and packed(lx=11) < 0 and packed(ld=5) < 0
+    assert packed(lx=6, ld=2) == packed() and b"dense_units <= 256" in L.knerf_last_error()
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "knerf.h")).read()
     for name, val in (("KNERF_TC_ORDERED", lib.TC_ORDERED), ("KNERF_BWD_DGRAD_ONLY", lib.BWD_DGRAD_ONLY),
                       ("KNERF_BWD_WGRAD_ONLY", lib.BWD_WGRAD_ONLY), ("KNERF_REC_FP8", lib.REC_FP8)):

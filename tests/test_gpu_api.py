@@ -147,7 +147,7 @@ def test_bf16_request_on_other_shape_falls_back_loudly(caplog):
     import keras_nerf_b200 as K
     from keras_nerf_b200.model.nerf import mlp as mlp_mod
     mlp_mod.set_seed(1)
-    m = K.NeRF(precision="bf16", n_layers=4, dense_units=128, skip_layer=2, pos_emb_xyz=6, pos_emb_dir=2)
+    m = K.NeRF(precision="bf16", n_layers=8, dense_units=128, skip_layer=2, pos_emb_xyz=6, pos_emb_dir=2)   # three concats
     with caplog.at_level(logging.WARNING):
         m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=8, image_width=16, ray_chunks=64,
                   white_background=True)

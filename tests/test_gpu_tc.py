@@ -565,3 +565,112 @@ def test_tc_shallower_model_equals_default_model_with_identity_layers():
     for a, b, n in pairs:
         x, y = g_s[a:a + n], g_b[b:b + n]
         assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-12, (a, b, n)
+
+
+WIDTHS = [(128, 8, 4), (64, 4, 2), (192, 6, 3), (100, 8, 4)]   # (dense_units, n_layers, skip_layer)
+
+
+@pytest.mark.parametrize("units,n_layers,skip", WIDTHS)
+def test_tc_narrower_models_vs_fp32(units, n_layers, skip):
+    """--num_units below 256 (train.py:27): the operands are zero-padded to the kernels' 256 columns -- relu(0) = 0 stays
+    0 through the chain -- and only the model's own rows / columns are flushed.  Forward and weight gradients against the
+    fp32 mode."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S = 512, 192
+    ms = []
+    for prec in ("fp32", "bf16"):
+        mlp_mod.set_seed(42)
+        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip, dense_units=units)
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == prec                       # no fall-back
+        ms.append(m)
+    assert torch.equal(ms[0].fine.params, ms[1].fine.params)
+    o, d, t, tgt = _rays(R, S, seed=23 + units)
+    grads, outs = {}, {}
+    for m in ms:
+        out = _fwd(m, m.fine, o, d, t, True)
+        outs[m.precision] = out
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        # guard bands around the gradient buffer: the kernels flush 256-wide accumulators into a narrower model's
+        # kernels -- nothing may land outside the model's own entries (compute-sanitizer is not available on this pool)
+        G, n = 4096, m.fine.params.numel()
+        guarded = torch.zeros(n + 2 * G, device=t.device)
+        gbuf = guarded[G:G + n]
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec_train, gbuf.data_ptr(), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        torch.cuda.synchronize()
+        assert float(guarded[:G].abs().max()) == 0.0 and float(guarded[G + n:].abs().max()) == 0.0
+        grads[m.precision] = gbuf.cpu()
+    ia, ib = _composite(outs["fp32"], t), _composite(outs["bf16"], t)
+    assert float((ia - ib).abs().max()) <= 2e-3
+    cfg = O.NerfConfig(n_layers=n_layers, skip_layer=skip, dense_units=units)
+    a, b = grads["fp32"], grads["bf16"]
+    assert a.numel() == O.param_count(cfg) and torch.isfinite(b).all()
+    off = 0
+    for name, fi, fo in O.layer_shapes(cfg):
+        for n in (fi * fo, fo):
+            x, y = a[off:off + n], b[off:off + n]
+            rel = float((x - y).norm() / x.norm().clamp_min(1e-30))
+            assert rel <= 4e-2, (name, rel)
+            off += n
+
+
+def test_tc_narrower_model_equals_zero_padded_default_model():
+    """Structure check of the width embedding: a 128-wide model IS the default model whose kernels are zero outside the
+    first 128 rows / columns of every hidden block -- bit-identical bf16 forward, equal gradients on the embedded
+    entries, and nothing written anywhere else."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200 import _lib
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    R, S, U = 300, 192, 128
+    mlp_mod.set_seed(7)
+    small = K.NeRF(precision="bf16", dense_units=U)
+    big = K.NeRF(precision="bf16")
+    for m in (small, big):
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
+                  white_background=True)
+        assert m.precision == "bf16"
+    cs, cb = O.NerfConfig(dense_units=U), O.NerfConfig()
+    ps = small.fine.params.cpu()
+    ps = ps + 0.01 * torch.randn(ps.numel(), generator=torch.Generator().manual_seed(1))
+    pb = torch.zeros(O.param_count(cb))
+    idx_small, idx_big = [], []                          # flat indices of corresponding entries
+    os_, ob = 0, 0
+    for (name, fs, fo_s), (_, fb, fo_b) in zip(O.layer_shapes(cs), O.layer_shapes(cb)):
+        hid_s, hid_b = (0, 0) if name == "layer_0" else ((U // 2, 128) if name == "rgb" else (U, 256))
+        rows_s = torch.arange(fs)
+        rows_b = torch.where(rows_s < hid_s, rows_s, rows_s - hid_s + hid_b)   # hidden rows first, the encoding rows behind
+        cols = torch.arange(fo_s)
+        i_s = os_ + rows_s[:, None] * fo_s + cols[None]
+        i_b = ob + rows_b[:, None] * fo_b + cols[None]
+        idx_small += [i_s.flatten(), os_ + fs * fo_s + cols]
+        idx_big += [i_b.flatten(), ob + fb * fo_b + cols]
+        os_, ob = os_ + fs * fo_s + fo_s, ob + fb * fo_b + fo_b
+    idx_small, idx_big = torch.cat(idx_small), torch.cat(idx_big)
+    assert idx_small.numel() == ps.numel() and os_ == ps.numel() and ob == pb.numel()
+    pb[idx_big] = ps[idx_small]
+    small.fine.params.copy_(ps.to(small.fine.params.device))
+    big.fine.params.copy_(pb.to(big.fine.params.device))
+    small._repack()
+    big._repack()
+    o, d, t, tgt = _rays(R, S, seed=11)
+    res = []
+    for m in (small, big):
+        out = _fwd(m, m.fine, o, d, t, True)
+        dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+        _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+                  2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dpre),
+                  R, S, m._prec_train, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        res.append((out.cpu(), gbuf.cpu()))
+    (out_s, g_s), (out_b, g_b) = res
+    assert torch.equal(out_s, out_b)
+    x, y = g_s[idx_small], g_b[idx_big]
+    assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max())
+    assert float(y.abs().max()) > 0
