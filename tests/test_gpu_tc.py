@@ -674,3 +674,30 @@ def test_tc_narrower_model_equals_zero_padded_default_model():
     x, y = g_s[idx_small], g_b[idx_big]
     assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max())
     assert float(y.abs().max()) > 0
+
+
+@pytest.mark.parametrize("k", [-40, -12, 9])
+def test_tc_fp8_records_are_scale_invariant(k):
+    """The e5m2 gradient records carry ONE power-of-two scale per backward call, taken from max|d_pre|: multiplying the
+    upstream gradient by 2^k must multiply every weight gradient by exactly 2^k (same mantissas everywhere; only the
+    order of the fp32 atomics differs) -- small losses late in training or large ray counts do not push the records
+    into the subnormals, large ones do not saturate them.  Zero upstream gradients give zero (finite) gradients."""
+    from keras_nerf_b200 import _lib
+    R, S = 300, 192
+    _, m = _models(R, records="fp8")
+    o, d, t, tgt = _rays(R, S, seed=29)
+    out = _fwd(m, m.fine, o, d, t, True)
+    dpre, sq = torch.empty(R, S, 4, device=t.device), torch.empty(R, device=t.device)
+    _lib.call("knerf_composite_backward", _lib.ptr(out), _lib.ptr(t), R, S, 1, 1, 1e-10, None, _lib.ptr(tgt),
+              2.0 / (3 * R), 1, _lib.ptr(dpre), _lib.ptr(sq), _lib.stream())
+    res = []
+    for scale in (1.0, 2.0 ** k, 0.0):
+        dp = (dpre * scale).contiguous()
+        gbuf = torch.zeros_like(m.fine.params)
+        _lib.call("knerf_mlp_backward", C.byref(m.cfg), _lib.ptr(m.fine.params), m._packed_ptr("fine"), _lib.ptr(dp),
+                  R, S, m._prec_train, _lib.ptr(gbuf), m._ws.data_ptr(), m._ws.numel(), _lib.stream())
+        res.append(gbuf.double().cpu())
+    g1, gk, g0 = res
+    assert torch.isfinite(gk).all() and float(g1.abs().max()) > 0
+    assert float((gk * 2.0 ** -k - g1).abs().max()) <= 1e-5 * float(g1.abs().max())
+    assert float(g0.abs().max()) == 0.0
