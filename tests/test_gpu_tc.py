@@ -470,8 +470,9 @@ def test_tc_fp8_records_vs_bf16_records():
 DEPTHS = [(6, 4), (6, 3), (4, 4), (7, 4), (8, 8), (2, 4), (1, 4)]   # (n_layers, skip_layer) the chain kernels can embed
 
 
+@pytest.mark.parametrize("records", RECORDS)
 @pytest.mark.parametrize("n_layers,skip", DEPTHS)
-def test_tc_other_depths_vs_fp32(n_layers, skip):
+def test_tc_other_depths_vs_fp32(n_layers, skip, records):
     """--num_layers / --skip_layer (train.py:26-28): models of up to eight 256-wide layers with at most one skip concat
     run on the same fused kernels -- the missing chain layers are identity layers, which are exact behind a ReLU
     (csrc/api.cu tc_chain_map).  Forward and weight gradients against the fp32 mode, as for the default model."""
@@ -482,7 +483,7 @@ def test_tc_other_depths_vs_fp32(n_layers, skip):
     ms = []
     for prec in ("fp32", "bf16"):
         mlp_mod.set_seed(42)
-        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip)
+        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip, records=records)
         m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
                   white_background=True)
         assert m.precision == prec                       # no fall-back
@@ -570,8 +571,9 @@ def test_tc_shallower_model_equals_default_model_with_identity_layers():
 WIDTHS = [(128, 8, 4), (64, 4, 2), (192, 6, 3), (100, 8, 4)]   # (dense_units, n_layers, skip_layer)
 
 
+@pytest.mark.parametrize("records", RECORDS)
 @pytest.mark.parametrize("units,n_layers,skip", WIDTHS)
-def test_tc_narrower_models_vs_fp32(units, n_layers, skip):
+def test_tc_narrower_models_vs_fp32(units, n_layers, skip, records):
     """--num_units below 256 (train.py:27): the operands are zero-padded to the kernels' 256 columns -- relu(0) = 0 stays
     0 through the chain -- and only the model's own rows / columns are flushed.  Forward and weight gradients against the
     fp32 mode."""
@@ -582,7 +584,7 @@ def test_tc_narrower_models_vs_fp32(units, n_layers, skip):
     ms = []
     for prec in ("fp32", "bf16"):
         mlp_mod.set_seed(42)
-        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip, dense_units=units)
+        m = K.NeRF(precision=prec, n_layers=n_layers, skip_layer=skip, dense_units=units, records=records)
         m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=1, image_width=R, ray_chunks=R,
                   white_background=True)
         assert m.precision == prec                       # no fall-back
