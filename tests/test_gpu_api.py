@@ -183,6 +183,37 @@ def test_bf16_train_step_with_fewer_encoding_frequencies():
     assert logs["bf16"][2]["coarse_loss"] != logs["bf16"][0]["coarse_loss"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_chunks_take_the_same_step(precision):
+    """compile(fuse_chunks=...): the ray chunks of a training step are independent and their gradients summed
+    (nerf.py:351-421), so executing several per library call must give the same losses and the same updated weights
+    (fp32 summation order apart) when the fine-sample draws are given explicitly."""
+    import keras_nerf_b200 as K
+    from keras_nerf_b200.model.nerf import mlp as mlp_mod
+    H = W = 16
+    rng = np.random.default_rng(0)
+    pose = K.pose_spherical(20.0, -30.0, 4.0)
+    o, d, t = K.RaysGenerator(K.get_focal_from_fov(0.69, W), W, H, 2.0, 6.0, 64)(pose, seed=3)
+    images = rng.uniform(0, 1, (1, H, W, 4)).astype(np.float32)
+    u_f = rng.uniform(0, 1, (H * W, 128)).astype(np.float32)
+    res = []
+    for fuse in (None, "auto", 4):
+        mlp_mod.set_seed(1)
+        m = K.NeRF(precision=precision, scan_mode="sequential")
+        m.compile(optimizer="adam", loss="mse", batch_size=1, image_height=H, image_width=W, ray_chunks=32,
+                  white_background=True, fuse_chunks=fuse)
+        assert (m._train_ray_chunks, m._train_chunks) == {None: (32, 8), "auto": (256, 1), 4: (128, 2)}[fuse]
+        logs = m.train_step((images, (o[None], d[None], t[None])), u_fine=u_f)
+        res.append((logs, m.coarse.params.cpu().clone(), m.fine.params.cpu().clone()))
+    tol = 1e-6 if precision == "fp32" else 2e-3        # bf16: tile boundaries move, so do single roundings
+    for logs, pc, pf in res[1:]:
+        for k in ("coarse_loss", "fine_loss"):
+            assert logs[k] == pytest.approx(res[0][0][k], rel=10 * tol)
+        # one Adam step moves every weight by about lr = 1e-3: compare the steps, not the weights
+        assert float((pc - res[0][1]).abs().max()) <= (2e-5 if precision == "fp32" else 2e-3)
+        assert float((pf - res[0][2]).abs().max()) <= (2e-5 if precision == "fp32" else 2e-3)
+
+
 def test_custom_loss_is_refused_and_initializers_accepted():
     import keras_nerf_b200 as K
     m = K.NeRF(precision="fp32")

@@ -67,6 +67,9 @@ def main(argv=None, multi_gpu=True):
     parser.add_argument('--log_freq', type=int, default=5 if multi_gpu else 1)
     parser.add_argument('--verbose', action='store_true')
     parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_tc'])
+    parser.add_argument('--fuse_chunks', type=str, default='auto',
+                        help="execute several ray chunks of a training step per library call: 'auto' (up to 32,768 rays), "
+                             "'off', or a count.  The chunks of a step are independent, so the step is the same")
     parser.add_argument('--records', type=str, default='fp8', choices=['fp8', 'bf16'],
                         help='bf16 mode: format of the activation / gradient records kept for the weight gradients')
     args = parser.parse_args(argv)
@@ -108,7 +111,9 @@ def main(argv=None, multi_gpu=True):
     logging.info("Last epoch: {}".format(last_epoch))
     nerf.compile(optimizer='adam', loss='mean_squared_error', batch_size=args.batch_size, image_width=args.img_wh,
                  image_height=args.img_wh, ray_chunks=args.ray_chunks, run_eagerly=args.eagerly,
-                 white_background=args.white_bg)
+                 white_background=args.white_bg,
+                 fuse_chunks=None if args.fuse_chunks == 'off' else
+                 ('auto' if args.fuse_chunks == 'auto' else int(args.fuse_chunks)))
     if strategy is not None:
         strategy.broadcast_parameters(nerf)
         nerf._repack()
