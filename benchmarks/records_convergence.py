@@ -2,7 +2,10 @@
 """Does training with fp8 records (KNERF_REC_FP8) converge like training with bf16 records?  Two identically seeded
 bf16-mode models, one per record format, take the same steps on the synthetic scene at the bench's training shape
 (32,768 rays per step, random windows of 100 views of 400 x 400); every `every` steps both are evaluated on the same
-held-out rays.  usage: python benchmarks/records_convergence.py [steps=600] [every=100]"""
+held-out rays.  With `spread` a third run repeats the bf16-records training with other fine-sample draws: the spread
+between two runs of the SAME format is the yardstick for the difference between the formats (trajectories at a constant
+learning rate of 1e-3 are chaotic: any perturbation, even the order of the fp32 atomics, separates them).
+usage: python benchmarks/records_convergence.py [steps=600] [every=100] [spread]"""
 import json
 import os
 import sys
@@ -28,7 +31,10 @@ def main():
     plan = [(int(rng.integers(0, 90)), int(rng.integers(0, 400 * 400 - R))) for _ in range(steps)]
     held = [scene.ray_batch(90 + k, R, offset=40000 + 9000 * k, seed=500 + k) for k in range(4)]   # views 90..93: never trained on
     out = {"steps": steps, "rays_per_step": R, "eval_rays": 4 * R}
-    for records in ("bf16", "fp8"):
+    variants = [("bf16", "bf16", 0), ("fp8", "fp8", 0)]
+    if len(sys.argv) > 3 and sys.argv[3] == "spread":
+        variants.append(("bf16_other_draws", "bf16", 1000003))
+    for tag, records, seed_off in variants:
         mlp_mod.set_seed(42)
         torch.manual_seed(0)
         m = NeRF(precision="bf16", device=dev, records=records)
@@ -39,7 +45,7 @@ def main():
         t0.record()
         for i, (k, off) in enumerate(plan):
             img, rays = scene.ray_batch(k, R, offset=off, seed=10000 + i)
-            m.train_step((img, rays), seed=7000 + i)
+            m.train_step((img, rays), seed=7000 + i + seed_off)
             if (i + 1) % every == 0 or i + 1 == steps:
                 mse = np.zeros(2)
                 for hi, hr in held:
@@ -49,7 +55,8 @@ def main():
                 curve.append({"step": i + 1, "val_coarse_psnr": round(float(-10 * np.log10(mse[0])), 3),
                               "val_fine_psnr": round(float(-10 * np.log10(mse[1])), 3)})
         t1.record(); torch.cuda.synchronize()
-        out[records] = {"curve": curve, "seconds_incl_eval": round(t0.elapsed_time(t1) / 1e3, 2)}
+        out[tag] = {"curve": curve, "seconds_incl_eval": round(t0.elapsed_time(t1) / 1e3, 2)}
+        del m
     print(json.dumps(out))
 
 
