@@ -119,6 +119,23 @@ def test_comm_entry_points_validate_arguments(lib):
     assert packed(units=128) == packed() and packed(units=64, n_layers=4, skip=2) == packed()   # zero-padded to 256
     assert packed(units=512) < 0 and packed(units=258) < 0 and packed(lx=11) < 0 and packed(ld=5) < 0
     assert packed(lx=6, ld=2) == packed() and b"dense_units <= 256" in L.knerf_last_error()
+
+    # the whole (n_layers, skip_layer) grid against the rule stated in DESIGN.md §2: layers taking the concat are i + 1
+    # for every skip point 0 < i < n_layers with i % skip == 0 (mlp.py:36-38); at most one of them, not the heads (i =
+    # n_layers - 1), it must fit at chain layer 5 (<= 5 layers in front of it, <= 2 behind)
+    def embeds(nl, sk):
+        if nl > 8:
+            return False
+        pts = [i for i in range(1, nl) if i % sk == 0]
+        if any(i == nl - 1 for i in pts):
+            return False
+        cons = [i + 1 for i in pts]
+        if len(cons) > 1:
+            return False
+        return not cons or (cons[0] <= 5 and nl - 1 - cons[0] <= 2)
+    for nl in range(1, 11):
+        for sk in range(1, 11):
+            assert (packed(nl, 256, sk) > 0) == embeds(nl, sk), (nl, sk)
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "knerf.h")).read()
     for name, val in (("KNERF_TC_ORDERED", lib.TC_ORDERED), ("KNERF_BWD_DGRAD_ONLY", lib.BWD_DGRAD_ONLY),
                       ("KNERF_BWD_WGRAD_ONLY", lib.BWD_WGRAD_ONLY), ("KNERF_REC_FP8", lib.REC_FP8)):
