@@ -294,9 +294,10 @@ __device__ __forceinline__ float* head_smem(uint8_t* xs) { return reinterpret_ca
 // rec8 (fp8 records): the tile's saved activation record goes to HBM from here, 16 columns per 16-byte vector,
 // rounded from the fp32 accumulator -- no copy of the operand tile, no hand-shake with a store warp.
 // one 32-column group of epi_hidden: v = the accumulator values (already waited for)
+// (returns the ReLU' bits of the 32 columns)
 template <bool TRAIN, bool REC8>
-__device__ __forceinline__ void epi_hidden_group(const uint32_t (&v)[32], int gI, uint8_t* __restrict__ hs, int h, int r,
-                                                 uint8_t* __restrict__ mask_out, uint8_t* __restrict__ rec8) {
+__device__ __forceinline__ uint32_t epi_hidden_group(const uint32_t (&v)[32], int gI, uint8_t* __restrict__ hs, int h, int r,
+                                                     uint8_t* __restrict__ rec8) {
   const int col0 = h * 128 + gI * 32;
   uint32_t mbits = 0u;
 #pragma unroll
@@ -317,7 +318,6 @@ __device__ __forceinline__ void epi_hidden_group(const uint32_t (&v)[32], int gI
     // next layer's A operand, in place; with bf16 records also the saved record (stored to HBM by warp 10)
     *reinterpret_cast<uint4*>(hs + ((col0 >> 3) + c8) * kChunkA + r * 16) = pk;
   }
-  if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint32_t*>(mask_out + (h * 4 + gI) * 512 + r * 4) = mbits;
   if (TRAIN && REC8 && rec8 != nullptr) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -328,6 +328,7 @@ __device__ __forceinline__ void epi_hidden_group(const uint32_t (&v)[32], int gI
       __stcs(reinterpret_cast<uint4*>(rec8 + ((col0 >> 4) + k) * kChunkA + r * 16), q);
     }
   }
+  return mbits;
 }
 
 template <bool TRAIN, bool REC8>
@@ -336,13 +337,17 @@ __device__ __noinline__ void epi_hidden(uint32_t tacc, uint8_t* __restrict__ hs,
   // (measured and dropped: a second accumulator group in flight, so that the TMEM load of the next 32 columns runs under
   //  the conversion of the current ones, and IMADs instead of integer adds for the flag additions -- no change in the
   //  kernel's time, which at this point moves with the power cap more than with the instruction count)
+  uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
 #pragma unroll 1
   for (int gI = 0; gI < 4; ++gI) {
     uint32_t v[32];
     tmem_ld32_issue(tacc + h * 128 + gI * 32, v);
     tmem_ld32_wait(v);
-    epi_hidden_group<TRAIN, REC8>(v, gI, hs, h, r, mask_out, rec8);
+    const uint32_t mb = epi_hidden_group<TRAIN, REC8>(v, gI, hs, h, r, rec8);
+    m0 = gI == 0 ? mb : m0; m1 = gI == 1 ? mb : m1; m2 = gI == 2 ? mb : m2; m3 = gI == 3 ? mb : m3;
   }
+  // the thread's 128 ReLU' bits leave as ONE 16-byte store (512 contiguous bytes per warp)
+  if (TRAIN && mask_out != nullptr) *reinterpret_cast<uint4*>(mask_out + h * 2048 + r * 16) = make_uint4(m0, m1, m2, m3);
 }
 
 // ---- the fused forward kernel ----------------------------------------------------------------------------

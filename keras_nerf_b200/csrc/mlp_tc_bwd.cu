@@ -241,8 +241,8 @@ tc_mlp_dgrad_kernel(const uint8_t* __restrict__ packed, const float4* __restrict
           // this thread's 4 x 32 columns BEFORE waiting for the MMA so that the latency overlaps it
           uint32_t mb[4] = {0u, 0u, 0u, 0u};
           if (active) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mb[i] = __ldg(reinterpret_cast<const uint32_t*>(mask + (h * 4 + i) * 512 + r * 4));
+            const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mask + h * 2048 + r * 16));
+            mb[0] = mv.x; mb[1] = mv.y; mb[2] = mv.z; mb[3] = mv.w;
           }
           mbar_wait_cluster(&sm.acc_ready[tl], acc_par[tl]);
           acc_par[tl] ^= 1;

@@ -130,8 +130,9 @@ constexpr int kRecH0 = 32768;                      // h0..h7       8 x 64 KB
 // (the rgb_features activations G are NOT saved: G = h7 W' + PE(dir) W_g[256:] + b' is linear in records that are saved
 //  anyway, so the rgb kernel's gradient G^T d(rgb_pre) = W'^T (h7^T d(rgb_pre)) + W_g[256:]^T (PE(dir)^T d(rgb_pre))
 //  + b' (x) sum d(rgb_pre) comes from three columns the weight-gradient kernel computes anyway -- tc_finish_kernel)
-constexpr int kRecMask = kRecH0 + 8 * kHSBytes;    // ReLU' bits of h0..h7: 8 x [2 halves][4 groups][128 rows] u32 = 32 KB
-constexpr int kMaskLayerBytes = 4096;              //   word (h, g, r): columns h*128 + g*32 + (0..31) of row r;
+constexpr int kRecMask = kRecH0 + 8 * kHSBytes;    // ReLU' bits of h0..h7: 8 x [2 halves][128 rows][4 groups] u32 = 32 KB
+constexpr int kMaskLayerBytes = 4096;              //   word (h, r, g): columns h*128 + g*32 + (0..31) of row r (one 16-byte
+                                                   //   vector per thread of the epilogues);
                                                    //   bit 8 t + q = column 4 q + t (q = 0..7, t = 0..3): byte t holds one
                                                    //   column of every group of four, so that a shift by 7 - q parks the
                                                    //   four flags of columns 4q..4q+3 in the byte msbs, where one prmt with
