@@ -283,11 +283,13 @@ constexpr int kNumTasks = 10;
 // the whole kernel at 50 / 80 / 110 / 140 / 178; 178 gives 217 + 36 + 43 = 296 items = exactly two per CTA.
 constexpr int kHeadsCost = 178;
 // fp8 records (build_task_table8): 64 KB and 16 MMAs per tile for a `big` task (cost 128), 40 KB / 8 MMAs for the two
-// encoding tasks, 38 KB / 12 narrow MMAs for the heads; 33 slabs -> 231 + 2 x 20 + 25 = 296 items = two per CTA
+// encoding tasks, 38 KB / 12 narrow MMAs for the heads; 66 slabs -> 462 + 2 x 41 + 48 = 592 items = four per CTA
+// (swept on the GPU, profiles/r02_fp8_records.md: the item count must be a multiple of the 148 CTAs -- a partly filled
+// extra round costs 4-35 % -- and four per CTA beat two by 1.5-2 %)
 #ifndef KNERF_WG8_X   // (scratch builds for the balance measurements pass the three numbers as macros)
 #define KNERF_WG8_X 80
-#define KNERF_WG8_H 100
-#define KNERF_WG8_S 33
+#define KNERF_WG8_H 94
+#define KNERF_WG8_S 66
 #endif
 constexpr int kXpartCost8 = KNERF_WG8_X;
 constexpr int kHeadsCost8 = KNERF_WG8_H;
