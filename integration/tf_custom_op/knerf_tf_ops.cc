@@ -192,6 +192,8 @@ class KnerfGenerateRaysOp : public tf::OpKernel {
 REGISTER_KERNEL_BUILDER(Name("KnerfGenerateRays").Device(tf::DEVICE_GPU).HostMemory("camera_params"), KnerfGenerateRaysOp);
 
 // ---- a9/a10: coarse + fine pass of one chunk -------------------------------------------------------------------
+// (`precision` goes to the C ABI as it is: a knerf_precision value with the per-call option bits of knerf.h OR-ed in,
+//  e.g. KNERF_BF16 | KNERF_REC_FP8 = 0x801 for the tensor-core mode with fp8 records between its training kernels)
 #define KNERF_MODEL_ATTRS                                                                                        \
   .Attr("n_coarse: int = 64").Attr("n_fine: int = 128").Attr("pos_emb_xyz: int = 10").Attr("pos_emb_dir: int = 4") \
   .Attr("n_layers: int = 8").Attr("dense_units: int = 256").Attr("skip_layer: int = 4")                           \
